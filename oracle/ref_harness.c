@@ -1,0 +1,158 @@
+/*
+ * ref_harness.c -- thin C shim around the UNMODIFIED reference header.
+ *
+ * TEST INFRASTRUCTURE ONLY (see mg_oracle.h).  This file contains no solver
+ * code of its own: it #includes /root/reference/mg_3d.h (via -I, never copied)
+ * and exports entry points that call the reference's functions the way its own
+ * drivers do -- every compute routine from inside `#pragma omp parallel`, with
+ * the per-thread norm partials square-summed (test_mg_3d.c:37-67,
+ * test_rb_gs_3d.c:56-101).  Built into oracle/_ref/libmg_ref.so by
+ * oracle/Makefile; it exists only where /root/reference exists.
+ */
+#include <stdio.h>
+#include <string.h>
+
+#define GRID_LENGTH (1.)
+#include "mg_3d.h"
+
+void ref_set_threads(int n) { omp_set_num_threads(n); }
+int ref_max_threads(void) { return omp_get_max_threads(); }
+
+void ref_set_dirichlet(double *v, int N, double h)
+{
+    setupBoundaryConditions(v, N, h);
+}
+
+void ref_smooth(double *v, const double *d, int N, double h, int iters,
+                int first_red)
+{
+#pragma omp parallel
+    {
+        if (first_red)
+            preSmoother(v, d, N, h, iters);
+        else
+            postSmoother(v, d, N, h, iters);
+    }
+}
+
+/* team norm exactly as the drivers form it */
+static double team_norm(const double *part, int n)
+{
+    double s = 0;
+    for (int t = 0; t < n; t++)
+        s += part[t] * part[t];
+    return sqrt(s);
+}
+
+double ref_residual(const double *v, const double *d, int N, double h,
+                    double *res)
+{
+    int nt = omp_get_max_threads();
+    double *part = calloc(nt, sizeof(double));
+#pragma omp parallel
+    {
+        part[omp_get_thread_num()] = calculateResidual(v, d, N, h, res);
+    }
+    double r = team_norm(part, nt);
+    free(part);
+    return r;
+}
+
+void ref_restrict(const double *r, int Nf, double *dc, int Nc)
+{
+#pragma omp parallel
+    {
+        restrictResidual(r, Nf, dc, Nc);
+    }
+}
+
+void ref_prolong_correct(const double *ec, int Nc, double *ef, int Nf)
+{
+#pragma omp parallel
+    {
+        prolongateAndCorrectError(ec, Nc, ef, Nf);
+    }
+}
+
+void ref_coarse_matrix(double *A, int N, double h)
+{
+    constructCoarseMatrixA(A, N, h);
+}
+void ref_lu_factor(double *a, int n) { convertToLU_InPlace(a, n); }
+void ref_lu_solve(const double *lu, int n, const double *b, double *x)
+{
+    solveWithLU(lu, n, b, x);
+}
+double ref_l2norm(const double *d, int n) { return GetL2NormOfVector(d, n); }
+
+/* ---- the test_mg_3d.c flow on the reference's own Solver* API ---- */
+
+static int g_live = 0;
+
+int ref_solver_open(int coarse, int levels, int gs, double **grid,
+                    double **rhs, double *h)
+{
+    char a1[32], a2[32], a3[32];
+    snprintf(a1, sizeof a1, "%d", coarse);
+    snprintf(a2, sizeof a2, "%d", levels);
+    snprintf(a3, sizeof a3, "%d", gs);
+    char *argv[4] = {"ref", a1, a2, a3};
+    SolverInitialize(4, argv);
+    int N = SolverGetDetails(grid, rhs, h);
+    g_live = 1;
+    return N;
+}
+
+void ref_solver_close(void)
+{
+    if (g_live)
+        SolverFinalize();
+    g_live = 0;
+}
+
+double *ref_level_u(int l) { return u[l]; }
+double *ref_level_d(int l) { return d[l]; }
+double *ref_level_r(int l) { return r[l]; }
+
+/* one V-cycle by the whole team; returns the team norm */
+double ref_vcycle(void)
+{
+    int nt = omp_get_max_threads();
+    double *part = calloc(nt, sizeof(double));
+#pragma omp parallel
+    {
+        part[omp_get_thread_num()] = SolverLinSolve();
+    }
+    double r = team_norm(part, nt);
+    free(part);
+    return r;
+}
+
+/* test_mg_3d.c:17-67; history[c] = norm after cycle c+1; returns cycles */
+int ref_solve(int coarse, int levels, int gs, double tol, int max_cycles,
+              double *history, double *init_norm, double *u_out,
+              double *seconds)
+{
+    double *grid, *rhs, h;
+    int N = ref_solver_open(coarse, levels, gs, &grid, &rhs, &h);
+    SolverSetupBoundaryConditions();
+    double init = SolverGetInitialResidual();
+    setupBoundaryConditions(grid, N, h);
+    if (init_norm)
+        *init_norm = init;
+    double cmp = init * tol, norm = 1e9;
+    int c = 0;
+    double t0 = omp_get_wtime();
+    while (norm > cmp && c < max_cycles) {
+        norm = ref_vcycle();
+        if (history)
+            history[c] = norm;
+        c++;
+    }
+    if (seconds)
+        *seconds = omp_get_wtime() - t0;
+    if (u_out)
+        memcpy(u_out, grid, sizeof(double) * (size_t)N * N * N);
+    ref_solver_close();
+    return c;
+}
