@@ -1,0 +1,146 @@
+/*
+ * mgb.h -- C ABI of libmgb.so: the 3D geometric-multigrid V-cycle hot path
+ * (red-black Gauss-Seidel, residual, full-weighting restriction, trilinear
+ * prolongation, dense-LU coarsest solve) as hand-written sm_100a CUDA.
+ *
+ * This is the drop-in boundary for knram06/multigrid_parallel's mg_3d.h: plain
+ * pointers and sizes, no C++/torch types.  Every entry point names the
+ * reference interface it replaces (file:line into the reference tree).  The
+ * host-side mirror of the reference's own API (SolverInitialize & co.) lives in
+ * multigrid_parallel_b200/compat/mg_3d.h and is written purely against this
+ * header.
+ *
+ * Conventions
+ *   - all grids are fp64; host arrays are in the reference's NATURAL layout
+ *     p = (i*nj + j)*nk + k, k contiguous (mg_3d.h:43-44); device storage is
+ *     colour-split and private to the library
+ *   - level 0 is the coarsest, level L-1 the finest (mg_3d.h:41)
+ *   - colour 1 = "red" = (i+j+k) odd, colour 0 = "black" (mg_3d.h:669-693)
+ *   - every function returns 0 on success, non-zero on failure;
+ *     mgb_last_error() then describes the failure.  There is NO CPU fallback:
+ *     without a usable CUDA device every call fails.
+ */
+#ifndef MGB_H
+#define MGB_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct mgb_solver mgb_solver;
+
+enum { MGB_U = 0, MGB_D = 1, MGB_R = 2 };          /* which level array   */
+enum { MGB_BLACK = 0, MGB_RED = 1 };               /* colours             */
+enum {                                             /* TimingInfo stages, mg_3d.h:136-137 */
+    MGB_ST_SMOOTH1 = 0, MGB_ST_RESID1 = 1, MGB_ST_RESTRICT = 2,
+    MGB_ST_RECURSE = 3, MGB_ST_PROLONG = 4, MGB_ST_SMOOTH2 = 5,
+    MGB_ST_RESID2 = 6, MGB_NUM_STAGES = 7
+};
+enum {                                             /* mgb_set_option keys */
+    MGB_OPT_GRAPH = 0,      /* 1: replay the V-cycle as one CUDA graph (default 1)        */
+    MGB_OPT_PROFILE = 1,    /* 1: per-stage CUDA-event timing, eager launches (default 0)  */
+    MGB_OPT_FUSE = 2,       /* 1: fused residual+restriction, r not stored (default 1)     */
+    MGB_OPT_GRAPH_LEVELS = 3/* only levels < this are graphed when PROFILE=1               */
+};
+
+/* ---- errors / device ---------------------------------------------------- */
+const char *mgb_last_error(void);
+int mgb_device_count(int *count);
+const char *mgb_version(void);
+
+/* ---- lifecycle ----------------------------------------------------------
+ * mgb_create replaces SolverInitialize (mg_3d.h:107-144: level sizes
+ * (c-1)*2^l+1, zeroed u/d/r per level, spacing = 1/(n_fine-1)) and the
+ * coarse-operator half of SolverGetDetails (mg_3d.h:281-288:
+ * constructCoarseMatrixA with the coarse spacing + convertToLU_InPlace,
+ * gauss_elim.h:9-29) -- built and factorised on the GPU, once.
+ * (ci,cj,ck) = coarsest-grid points per axis, each 2^m+1; the reference only
+ * has cubes (ci=cj=ck).  spacing h = 1/(nk_fine-1). */
+int mgb_create(mgb_solver **out, int ci, int cj, int ck, int levels,
+               int gs_iters, int device);
+int mgb_destroy(mgb_solver *s);
+int mgb_levels(const mgb_solver *s);
+int mgb_dims(const mgb_solver *s, int level, int *ni, int *nj, int *nk);
+double mgb_spacing(const mgb_solver *s, int level);
+int mgb_set_option(mgb_solver *s, int key, int value);
+int mgb_sync(mgb_solver *s);
+
+/* ---- level arrays: the reference hands out raw host pointers u[l], d[l],
+ * r[l] (mg_3d.h:26, 278-279); here they cross the boundary explicitly.
+ * `host` is natural layout, ni*nj*nk doubles; pinned or pageable. */
+int mgb_upload(mgb_solver *s, int level, int which, const double *host);
+int mgb_download(mgb_solver *s, int level, int which, double *host);
+int mgb_zero(mgb_solver *s, int level, int which);
+/* setupBoundaryConditions (mg_3d.h:1147-1239) on the device array */
+int mgb_set_dirichlet(mgb_solver *s, int level, int which);
+/* GetL2NormOfVector (mg_3d.h:783-792): sum of squares over ALL points */
+int mgb_sumsq(mgb_solver *s, int level, int which, double *sumsq);
+/* test_mg_3d.c:78-97: sum over all points of (u - BCFunc)^2 at the finest level */
+int mgb_error_sumsq(mgb_solver *s, double *sumsq);
+
+/* ---- operators, one level at a time -------------------------------------
+ * mgb_half_sweep : one colour of smoothenAtIndex over the interior
+ *                  (mg_3d.h:432-443, loops 658-702)
+ * mgb_smooth     : preSmoother (first_red=1, mg_3d.h:640-709) or
+ *                  postSmoother (first_red=0, mg_3d.h:711-781)
+ * mgb_residual   : calculateResidual (mg_3d.h:794-842); store_r=0 is the
+ *                  res==NULL form; *sumsq = sum of diff^2 (caller takes sqrt)
+ * mgb_restrict   : restrictResidual r[level] -> d[level-1] (mg_3d.h:844-998)
+ * mgb_residual_restrict : the two above fused, r[level] not stored
+ * mgb_prolong_correct   : prolongateAndCorrectError u[level-1] -> u[level]
+ *                  (mg_3d.h:1000-1145)
+ * mgb_coarse_solve      : solveWithLU on level 0 (gauss_elim.h:31-60) */
+int mgb_half_sweep(mgb_solver *s, int level, int colour);
+int mgb_smooth(mgb_solver *s, int level, int iters, int first_red);
+int mgb_residual(mgb_solver *s, int level, int store_r, double *sumsq);
+int mgb_restrict(mgb_solver *s, int level);
+int mgb_residual_restrict(mgb_solver *s, int level);
+int mgb_prolong_correct(mgb_solver *s, int level);
+int mgb_coarse_solve(mgb_solver *s);
+/* the factorised coarse operator, row-major n x n (n = ci*cj*ck) */
+int mgb_coarse_lu_download(mgb_solver *s, double *host_lu);
+
+/* ---- the V-cycle ---------------------------------------------------------
+ * mgb_vcycle = SolverLinSolve -> vcycle (mg_3d.h:1415-1420, 1242-1362): one
+ * V(gs,gs) cycle from the finest level; *sumsq = squared 2-norm of the
+ * post-smoothing residual (the reference returns per-thread sqrt partials whose
+ * squares the driver sums, test_mg_3d.c:45-59).
+ * mgb_solve = the driver loop test_mg_3d.c:40-66: cycle while
+ * sqrt(sumsq) > threshold; history[c] = norm after cycle c+1. */
+int mgb_vcycle(mgb_solver *s, double *sumsq);
+int mgb_solve(mgb_solver *s, double threshold, int max_cycles,
+              double *history, int *cycles);
+
+/* ---- timing_info.h feed: accumulated seconds and call counts per level and
+ * stage (mg_3d.h:1279-1359), measured with CUDA events when MGB_OPT_PROFILE=1 */
+int mgb_timing(mgb_solver *s, int level, int stage, int *calls, double *seconds);
+int mgb_timing_reset(mgb_solver *s);
+/* number of kernel launches (graph nodes included) issued since creation */
+long long mgb_launch_count(const mgb_solver *s);
+
+/* ---- stateless array entry points for the reference's raw-pointer API
+ * (test_rb_gs_3d.c:70-81 and test_lu.c:33-42 call these on caller-owned host
+ * arrays).  Each call stages host -> device, runs the CUDA kernels, stages
+ * back; nothing is computed on the host. */
+int mgb_host_smooth(double *v, const double *d, int ni, int nj, int nk,
+                    double h, int iters, int first_red);
+int mgb_host_residual(const double *v, const double *d, int ni, int nj, int nk,
+                      double h, double *res /* may be NULL */, double *sumsq);
+int mgb_host_restrict(const double *r, int nif, int njf, int nkf, double *dc,
+                      int nic, int njc, int nkc);
+int mgb_host_prolong_correct(const double *ec, int nic, int njc, int nkc,
+                             double *ef, int nif, int njf, int nkf);
+int mgb_host_coarse_matrix(double *A, int ni, int nj, int nk, double h);
+int mgb_host_lu_factor(double *a, int n);
+int mgb_host_lu_solve(const double *lu, int n, const double *b, double *x);
+
+/* ---- resident single-grid session for the RB-GS microbenchmark
+ * (test_rb_gs_3d.c flow: one grid, no hierarchy).  A 1-level solver:
+ * mgb_create(.., levels=1, ..) gives u/d/r on the finest grid only and no
+ * coarse operator is built when ci*cj*ck exceeds MGB_MAX_DENSE_N. */
+#define MGB_MAX_DENSE_N 8192
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MGB_H */

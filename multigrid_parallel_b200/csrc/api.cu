@@ -1,0 +1,993 @@
+// api.cu -- the extern "C" boundary (include/mgb.h) and the host-side V-cycle
+// driver: level hierarchy in HBM, launch sequence of one V-cycle
+// (mg_3d.h:1242-1362), CUDA-graph replay, CUDA-event stage timing.
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/mgb.h"
+#include "kernels.h"
+
+using namespace mgb;
+
+// ----------------------------------------------------------------------------
+// errors
+// ----------------------------------------------------------------------------
+static thread_local std::string g_err;
+
+static int fail(const char *fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return 1;
+}
+
+#define CK(call)                                                                  \
+    do {                                                                          \
+        cudaError_t e_ = (call);                                                  \
+        if (e_ != cudaSuccess)                                                    \
+            return fail("%s:%d: %s -> %s", __FILE__, __LINE__, #call,             \
+                        cudaGetErrorString(e_));                                  \
+    } while (0)
+
+#define CKLAUNCH() CK(cudaGetLastError())
+
+extern "C" const char *mgb_last_error(void) { return g_err.c_str(); }
+extern "C" const char *mgb_version(void) { return "mgb 0.1 (sm_100a, colour-split fp64)"; }
+
+extern "C" int mgb_device_count(int *count)
+{
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) {
+        *count = 0;
+        return fail("cudaGetDeviceCount: %s", cudaGetErrorString(e));
+    }
+    *count = n;
+    return 0;
+}
+
+// ----------------------------------------------------------------------------
+// a colour-split array in device memory
+// ----------------------------------------------------------------------------
+struct DevArray {
+    void *alloc = nullptr;
+    double *base = nullptr;  // colour 0, local plane 0
+    size_t bytes = 0;
+};
+
+static Geo make_geo(int ni, int nj, int nk, int li, int i0)
+{
+    Geo g;
+    g.ni = ni; g.nj = nj; g.nk = nk;
+    g.li = li; g.i0 = i0;
+    g.kh = mgb_half_pitch(nk);
+    g.pj = (long long)nj * g.kh;
+    g.cs = ((long long)li * g.pj + 15) & ~15LL;
+    return g;
+}
+
+static int dev_alloc(const Geo &g, DevArray *a)
+{
+    a->bytes = sizeof(double) * (size_t)(2 * g.cs + 2 * MGB_GUARD);
+    CK(cudaMalloc(&a->alloc, a->bytes));
+    CK(cudaMemset(a->alloc, 0, a->bytes));
+    a->base = (double *)a->alloc + MGB_GUARD;
+    return 0;
+}
+
+static void dev_free(DevArray *a)
+{
+    if (a->alloc)
+        cudaFree(a->alloc);
+    a->alloc = nullptr;
+    a->base = nullptr;
+}
+
+struct Level {
+    Geo g;
+    double h, hSq, invHsq;
+    DevArray a[3];  // MGB_U, MGB_D, MGB_R
+};
+
+struct StageMark {
+    int level, stage;
+    cudaEvent_t a, b;
+};
+
+struct mgb_solver {
+    int device = 0;
+    int L = 0, gs = 0;
+    std::vector<Level> lv;
+    cudaStream_t st = nullptr;
+    double *partials = nullptr;
+    double *d_scal = nullptr;  // device scalars
+    double *h_scal = nullptr;  // pinned mirror
+    double *stage = nullptr;   // natural-layout staging buffer
+    size_t stage_n = 0;
+    // coarsest operator
+    int nc = 0;
+    double *lu = nullptr, *lut = nullptr, *cb = nullptr, *cx = nullptr;
+    // options
+    int opt_graph = 1, opt_profile = 0, opt_fuse = 1;
+    cudaGraphExec_t gexec = nullptr;
+    long long graph_launches = 0;
+    // bookkeeping
+    long long launches = 0;
+    std::vector<double> secs;  // L*7
+    std::vector<int> calls;    // L*7
+    std::vector<cudaEvent_t> ev_pool;
+    size_t ev_used = 0;
+    std::vector<StageMark> marks;
+};
+
+struct LaunchScope {
+    mgb_solver *s;
+    long long start;
+    explicit LaunchScope(mgb_solver *s_) : s(s_), start(launches_issued()) {}
+    ~LaunchScope() { s->launches += launches_issued() - start; }
+};
+
+static int bind(const mgb_solver *s)
+{
+    if (!s)
+        return fail("null solver");
+    CK(cudaSetDevice(s->device));
+    return 0;
+}
+
+static int check_level(const mgb_solver *s, int level, int which)
+{
+    if (level < 0 || level >= s->L)
+        return fail("level %d out of range [0,%d)", level, s->L);
+    if (which < 0 || which > 2)
+        return fail("array selector %d out of range", which);
+    return 0;
+}
+
+// ----------------------------------------------------------------------------
+// lifecycle
+// ----------------------------------------------------------------------------
+extern "C" int mgb_destroy(mgb_solver *s)
+{
+    if (!s)
+        return 0;
+    cudaSetDevice(s->device);
+    if (s->st)
+        cudaStreamSynchronize(s->st);
+    if (s->gexec)
+        cudaGraphExecDestroy(s->gexec);
+    for (auto &l : s->lv)
+        for (int w = 0; w < 3; w++)
+            dev_free(&l.a[w]);
+    for (auto e : s->ev_pool)
+        cudaEventDestroy(e);
+    if (s->partials) cudaFree(s->partials);
+    if (s->d_scal) cudaFree(s->d_scal);
+    if (s->h_scal) cudaFreeHost(s->h_scal);
+    if (s->stage) cudaFree(s->stage);
+    if (s->lu) cudaFree(s->lu);
+    if (s->lut) cudaFree(s->lut);
+    if (s->cb) cudaFree(s->cb);
+    if (s->cx) cudaFree(s->cx);
+    if (s->st) cudaStreamDestroy(s->st);
+    delete s;
+    return 0;
+}
+
+static bool pow2plus1(int n)
+{
+    return n >= 3 && ((n - 1) & (n - 2)) == 0;
+}
+
+extern "C" int mgb_create(mgb_solver **out, int ci, int cj, int ck, int levels,
+                          int gs_iters, int device)
+{
+    if (!out)
+        return fail("out is null");
+    *out = nullptr;
+    if (levels < 1 || levels > 24)
+        return fail("levels=%d out of range", levels);
+    if (ci < 3 || cj < 3 || ck < 3)
+        return fail("coarse extents must be >= 3 (got %d %d %d)", ci, cj, ck);
+    // mg_3d.h:120-123: (coarse-1) must be a power of two (only enforced when a
+    // hierarchy is actually built)
+    if (levels > 1 && !(pow2plus1(ci) && pow2plus1(cj) && pow2plus1(ck)))
+        return fail("coarse extents minus one must be powers of two (got %d %d %d)", ci,
+                    cj, ck);
+    if (gs_iters < 0)
+        return fail("gs_iters < 0");
+    int ndev = 0;
+    if (mgb_device_count(&ndev))
+        return 1;
+    if (ndev < 1)
+        return fail("no CUDA device: libmgb has no CPU fallback");
+    if (device < 0 || device >= ndev)
+        return fail("device %d out of range [0,%d)", device, ndev);
+    const long long nfine_k = (long long)(ck - 1) * (1LL << (levels - 1)) + 1;
+    const long long nfine_j = (long long)(cj - 1) * (1LL << (levels - 1)) + 1;
+    const long long nfine_i = (long long)(ci - 1) * (1LL << (levels - 1)) + 1;
+    if (nfine_k > 1 << 20 || nfine_j > 1 << 20 || nfine_i > 1 << 20)
+        return fail("grid too large");
+
+    mgb_solver *s = new mgb_solver();
+    s->device = device;
+    s->L = levels;
+    s->gs = gs_iters;
+    cudaError_t e = cudaSetDevice(device);
+    if (e != cudaSuccess) {
+        delete s;
+        return fail("cudaSetDevice(%d): %s", device, cudaGetErrorString(e));
+    }
+#define CKD(call)                                                                 \
+    do {                                                                          \
+        cudaError_t e_ = (call);                                                  \
+        if (e_ != cudaSuccess) {                                                  \
+            fail("%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+            mgb_destroy(s);                                                       \
+            return 1;                                                             \
+        }                                                                         \
+    } while (0)
+    CKD(cudaStreamCreateWithFlags(&s->st, cudaStreamNonBlocking));
+    CKD(cudaMalloc(&s->partials, sizeof(double) * kMaxPartials));
+    CKD(cudaMalloc(&s->d_scal, sizeof(double) * 16));
+    CKD(cudaMemset(s->d_scal, 0, sizeof(double) * 16));
+    CKD(cudaMallocHost(&s->h_scal, sizeof(double) * 16));
+
+    s->lv.resize(levels);
+    const double hfine = 1. / (double)(nfine_k - 1);  // mg_3d.h:143 with GRID_LENGTH=1
+    for (int l = 0; l < levels; l++) {
+        Level &lv = s->lv[l];
+        const int ni = (ci - 1) * (1 << l) + 1;  // mg_3d.h:41
+        const int nj = (cj - 1) * (1 << l) + 1;
+        const int nk = (ck - 1) * (1 << l) + 1;
+        lv.g = make_geo(ni, nj, nk, ni, 0);
+        // h_l = h_fine * 2^(L-1-l), formed by repeated doubling like
+        // mg_3d.h:1303 (exact in binary either way)
+        double h = hfine;
+        for (int t = levels - 1; t > l; t--)
+            h = 2 * h;
+        lv.h = h;
+        lv.hSq = h * h;            // mg_3d.h:644
+        lv.invHsq = 1. / (h * h);  // mg_3d.h:797
+        for (int w = 0; w < 3; w++)
+            if (dev_alloc(lv.g, &lv.a[w])) {
+                mgb_destroy(s);
+                return 1;
+            }
+    }
+    s->secs.assign((size_t)levels * MGB_NUM_STAGES, 0.);
+    s->calls.assign((size_t)levels * MGB_NUM_STAGES, 0);
+
+    // coarsest operator (mg_3d.h:281-288), built + factorised on the device
+    const long long nc = (long long)ci * cj * ck;
+    if (nc <= MGB_MAX_DENSE_N) {
+        s->nc = (int)nc;
+        CKD(cudaMalloc(&s->lu, sizeof(double) * nc * nc));
+        CKD(cudaMalloc(&s->lut, sizeof(double) * nc * nc));
+        CKD(cudaMalloc(&s->cb, sizeof(double) * nc));
+        CKD(cudaMalloc(&s->cx, sizeof(double) * nc));
+        LaunchScope ls(s);
+        launch_coarse_matrix(s->lu, ci, cj, ck, s->lv[0].h, s->st);
+        launch_lu_factor(s->lu, s->nc, s->st);
+        launch_transpose(s->lu, s->lut, s->nc, s->st);
+        CKD(cudaGetLastError());
+        CKD(cudaStreamSynchronize(s->st));
+    } else if (levels > 1) {
+        mgb_destroy(s);
+        return fail("coarsest grid has %lld unknowns > MGB_MAX_DENSE_N", nc);
+    }
+#undef CKD
+    *out = s;
+    return 0;
+}
+
+extern "C" int mgb_levels(const mgb_solver *s) { return s ? s->L : 0; }
+
+extern "C" int mgb_dims(const mgb_solver *s, int level, int *ni, int *nj, int *nk)
+{
+    if (!s)
+        return fail("null solver");
+    if (check_level(s, level, 0))
+        return 1;
+    *ni = s->lv[level].g.ni;
+    *nj = s->lv[level].g.nj;
+    *nk = s->lv[level].g.nk;
+    return 0;
+}
+
+extern "C" double mgb_spacing(const mgb_solver *s, int level)
+{
+    if (!s || level < 0 || level >= s->L)
+        return 0.;
+    return s->lv[level].h;
+}
+
+static void drop_graph(mgb_solver *s)
+{
+    if (s->gexec) {
+        cudaGraphExecDestroy(s->gexec);
+        s->gexec = nullptr;
+    }
+}
+
+extern "C" int mgb_set_option(mgb_solver *s, int key, int value)
+{
+    if (bind(s))
+        return 1;
+    switch (key) {
+    case MGB_OPT_GRAPH: s->opt_graph = value != 0; break;
+    case MGB_OPT_PROFILE: s->opt_profile = value != 0; break;
+    case MGB_OPT_FUSE: s->opt_fuse = value != 0; drop_graph(s); break;
+    case MGB_OPT_GRAPH_LEVELS: break;
+    default: return fail("unknown option %d", key);
+    }
+    return 0;
+}
+
+extern "C" int mgb_sync(mgb_solver *s)
+{
+    if (bind(s))
+        return 1;
+    CK(cudaStreamSynchronize(s->st));
+    return 0;
+}
+
+// ----------------------------------------------------------------------------
+// level arrays across the boundary
+// ----------------------------------------------------------------------------
+static int need_stage(mgb_solver *s, size_t n)
+{
+    if (s->stage_n >= n)
+        return 0;
+    if (s->stage) {
+        CK(cudaStreamSynchronize(s->st));
+        CK(cudaFree(s->stage));
+        s->stage = nullptr;
+        s->stage_n = 0;
+    }
+    CK(cudaMalloc(&s->stage, sizeof(double) * n));
+    s->stage_n = n;
+    return 0;
+}
+
+extern "C" int mgb_upload(mgb_solver *s, int level, int which, const double *host)
+{
+    if (bind(s) || check_level(s, level, which))
+        return 1;
+    if (!host)
+        return fail("host pointer is null");
+    Level &lv = s->lv[level];
+    const size_t n = (size_t)lv.g.ni * lv.g.nj * lv.g.nk;
+    if (need_stage(s, n))
+        return 1;
+    LaunchScope ls(s);
+    CK(cudaMemcpyAsync(s->stage, host, sizeof(double) * n, cudaMemcpyHostToDevice, s->st));
+    launch_pack(lv.g, s->stage, lv.a[which].base, s->st);
+    CKLAUNCH();
+    CK(cudaStreamSynchronize(s->st));
+    return 0;
+}
+
+extern "C" int mgb_download(mgb_solver *s, int level, int which, double *host)
+{
+    if (bind(s) || check_level(s, level, which))
+        return 1;
+    if (!host)
+        return fail("host pointer is null");
+    Level &lv = s->lv[level];
+    const size_t n = (size_t)lv.g.ni * lv.g.nj * lv.g.nk;
+    if (need_stage(s, n))
+        return 1;
+    LaunchScope ls(s);
+    launch_unpack(lv.g, lv.a[which].base, s->stage, s->st);
+    CKLAUNCH();
+    CK(cudaMemcpyAsync(host, s->stage, sizeof(double) * n, cudaMemcpyDeviceToHost, s->st));
+    CK(cudaStreamSynchronize(s->st));
+    return 0;
+}
+
+extern "C" int mgb_zero(mgb_solver *s, int level, int which)
+{
+    if (bind(s) || check_level(s, level, which))
+        return 1;
+    Level &lv = s->lv[level];
+    CK(cudaMemsetAsync(lv.a[which].base, 0, sizeof(double) * 2 * lv.g.cs, s->st));
+    return 0;
+}
+
+extern "C" int mgb_set_dirichlet(mgb_solver *s, int level, int which)
+{
+    if (bind(s) || check_level(s, level, which))
+        return 1;
+    Level &lv = s->lv[level];
+    LaunchScope ls(s);
+    launch_set_dirichlet(lv.g, lv.a[which].base, lv.h, s->st);
+    CKLAUNCH();
+    return 0;
+}
+
+static int fetch_scalar(mgb_solver *s, int slot, double *out)
+{
+    CK(cudaMemcpyAsync(s->h_scal + slot, s->d_scal + slot, sizeof(double),
+                       cudaMemcpyDeviceToHost, s->st));
+    CK(cudaStreamSynchronize(s->st));
+    *out = s->h_scal[slot];
+    return 0;
+}
+
+extern "C" int mgb_sumsq(mgb_solver *s, int level, int which, double *sumsq)
+{
+    if (bind(s) || check_level(s, level, which))
+        return 1;
+    Level &lv = s->lv[level];
+    LaunchScope ls(s);
+    launch_sumsq(lv.a[which].base, 2 * lv.g.cs, s->partials, s->d_scal + 1, s->st);
+    CKLAUNCH();
+    return fetch_scalar(s, 1, sumsq);
+}
+
+extern "C" int mgb_error_sumsq(mgb_solver *s, double *sumsq)
+{
+    if (bind(s))
+        return 1;
+    Level &lv = s->lv[s->L - 1];
+    LaunchScope ls(s);
+    launch_error_sumsq(lv.g, lv.a[MGB_U].base, lv.h, s->partials, s->d_scal + 2, s->st);
+    CKLAUNCH();
+    return fetch_scalar(s, 2, sumsq);
+}
+
+// ----------------------------------------------------------------------------
+// operators (enqueue only; the caller of the C entry point synchronises)
+// ----------------------------------------------------------------------------
+static void q_half_sweep(mgb_solver *s, int q, int colour)
+{
+    Level &lv = s->lv[q];
+    launch_half_sweep(lv.g, lv.a[MGB_U].base, lv.a[MGB_D].base, lv.hSq, colour, 1,
+                      lv.g.li - 1, s->st);
+}
+
+static void q_smooth(mgb_solver *s, int q, int iters, int first_red)
+{
+    for (int it = 0; it < iters; it++) {
+        q_half_sweep(s, q, first_red ? 1 : 0);
+        q_half_sweep(s, q, first_red ? 0 : 1);
+    }
+}
+
+static void q_residual(mgb_solver *s, int q, bool store, int slot)
+{
+    Level &lv = s->lv[q];
+    launch_residual(lv.g, lv.a[MGB_U].base, lv.a[MGB_D].base,
+                    store ? lv.a[MGB_R].base : nullptr, lv.invHsq, 1, lv.g.li - 1,
+                    s->partials, s->d_scal + slot, s->st);
+}
+
+static void q_restrict(mgb_solver *s, int q)
+{
+    Level &f = s->lv[q], &c = s->lv[q - 1];
+    launch_restrict(f.g, f.a[MGB_R].base, c.g, c.a[MGB_D].base, 0, c.g.li, s->st);
+}
+
+static void q_residual_restrict(mgb_solver *s, int q)
+{
+    // single-pass fused kernel not in yet: residual into r, then restrict
+    q_residual(s, q, true, 3);
+    q_restrict(s, q);
+}
+
+static void q_prolong(mgb_solver *s, int q)
+{
+    Level &f = s->lv[q], &c = s->lv[q - 1];
+    launch_prolong_correct(c.g, c.a[MGB_U].base, f.g, f.a[MGB_U].base, 0, f.g.li, s->st);
+}
+
+static void q_coarse_solve(mgb_solver *s)
+{
+    // solveWithLU(LU, n, d[0], u[0]) (mg_3d.h:1270): the dense vectors are the
+    // natural-layout views of level 0
+    Level &lv = s->lv[0];
+    launch_unpack(lv.g, lv.a[MGB_D].base, s->cb, s->st);
+    launch_lu_solve(s->lu, s->lut, s->nc, s->cb, s->cx, s->st);
+    launch_pack(lv.g, s->cx, lv.a[MGB_U].base, s->st);
+}
+
+#define OP_PROLOGUE(level_expr, min_level)                                        \
+    if (bind(s))                                                                  \
+        return 1;                                                                 \
+    if ((level_expr) < (min_level) || (level_expr) >= s->L)                       \
+        return fail("level %d out of range [%d,%d)", (level_expr), (min_level), s->L); \
+    LaunchScope ls(s)
+
+extern "C" int mgb_half_sweep(mgb_solver *s, int level, int colour)
+{
+    OP_PROLOGUE(level, 0);
+    q_half_sweep(s, level, colour ? 1 : 0);
+    CKLAUNCH();
+    return 0;
+}
+
+extern "C" int mgb_smooth(mgb_solver *s, int level, int iters, int first_red)
+{
+    OP_PROLOGUE(level, 0);
+    q_smooth(s, level, iters, first_red);
+    CKLAUNCH();
+    return 0;
+}
+
+extern "C" int mgb_residual(mgb_solver *s, int level, int store_r, double *sumsq)
+{
+    OP_PROLOGUE(level, 0);
+    q_residual(s, level, store_r != 0, 0);
+    CKLAUNCH();
+    if (sumsq)
+        return fetch_scalar(s, 0, sumsq);
+    return 0;
+}
+
+extern "C" int mgb_restrict(mgb_solver *s, int level)
+{
+    OP_PROLOGUE(level, 1);
+    q_restrict(s, level);
+    CKLAUNCH();
+    return 0;
+}
+
+extern "C" int mgb_residual_restrict(mgb_solver *s, int level)
+{
+    OP_PROLOGUE(level, 1);
+    q_residual_restrict(s, level);
+    CKLAUNCH();
+    return 0;
+}
+
+extern "C" int mgb_prolong_correct(mgb_solver *s, int level)
+{
+    OP_PROLOGUE(level, 1);
+    q_prolong(s, level);
+    CKLAUNCH();
+    return 0;
+}
+
+extern "C" int mgb_coarse_solve(mgb_solver *s)
+{
+    if (bind(s))
+        return 1;
+    if (!s->lu)
+        return fail("no coarse operator (single-grid session)");
+    LaunchScope ls(s);
+    q_coarse_solve(s);
+    CKLAUNCH();
+    return 0;
+}
+
+extern "C" int mgb_coarse_lu_download(mgb_solver *s, double *host_lu)
+{
+    if (bind(s))
+        return 1;
+    if (!s->lu)
+        return fail("no coarse operator (single-grid session)");
+    CK(cudaStreamSynchronize(s->st));
+    CK(cudaMemcpy(host_lu, s->lu, sizeof(double) * (size_t)s->nc * s->nc,
+                  cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+// ----------------------------------------------------------------------------
+// the V-cycle (mg_3d.h:1242-1362)
+// ----------------------------------------------------------------------------
+static cudaEvent_t take_event(mgb_solver *s)
+{
+    if (s->ev_used == s->ev_pool.size()) {
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        s->ev_pool.push_back(e);
+    }
+    return s->ev_pool[s->ev_used++];
+}
+
+struct StageTimer {
+    mgb_solver *s;
+    bool on;
+    int level, stage;
+    cudaEvent_t a = nullptr;
+    StageTimer(mgb_solver *s_, bool on_, int level_, int stage_)
+        : s(s_), on(on_), level(level_), stage(stage_)
+    {
+        s->calls[(size_t)level * MGB_NUM_STAGES + stage]++;
+        if (on) {
+            a = take_event(s);
+            cudaEventRecord(a, s->st);
+        }
+    }
+    ~StageTimer()
+    {
+        if (on) {
+            cudaEvent_t b = take_event(s);
+            cudaEventRecord(b, s->st);
+            s->marks.push_back({level, stage, a, b});
+        }
+    }
+};
+
+// enqueue one cycle from level q down and back up; `count` = bump call counts
+// and (if timed) record stage events.  The residual norm of the finest level
+// lands in d_scal[0].
+static void enqueue_cycle(mgb_solver *s, int q, bool timed)
+{
+    Level &lv = s->lv[q];
+    if (q < s->L - 1)  // 1254-1260: coarse levels start from a zero guess
+        cudaMemsetAsync(lv.a[MGB_U].base, 0, sizeof(double) * 2 * lv.g.cs, s->st);
+    if (q == 0) {  // 1262-1277
+        StageTimer t(s, timed, 0, MGB_ST_RECURSE);
+        q_coarse_solve(s);
+        return;
+    }
+    {
+        StageTimer t(s, timed, q, MGB_ST_SMOOTH1);  // 1282
+        q_smooth(s, q, s->gs, 1);
+    }
+    if (s->opt_fuse) {
+        StageTimer t(s, timed, q, MGB_ST_RESID1);  // 1294 + 1310 in one pass
+        q_residual_restrict(s, q);
+        s->calls[(size_t)q * MGB_NUM_STAGES + MGB_ST_RESTRICT]++;
+    } else {
+        {
+            StageTimer t(s, timed, q, MGB_ST_RESID1);  // 1294
+            q_residual(s, q, true, 3);
+        }
+        {
+            StageTimer t(s, timed, q, MGB_ST_RESTRICT);  // 1310
+            q_restrict(s, q);
+        }
+    }
+    {
+        StageTimer t(s, timed, q, MGB_ST_RECURSE);  // 1320
+        enqueue_cycle(s, q - 1, timed);
+    }
+    {
+        StageTimer t(s, timed, q, MGB_ST_PROLONG);  // 1331
+        q_prolong(s, q);
+    }
+    {
+        StageTimer t(s, timed, q, MGB_ST_SMOOTH2);  // 1341
+        q_smooth(s, q, s->gs, 0);
+    }
+    {
+        // 1354: the reference evaluates the norm on every level but only the
+        // finest one is ever used (test_mg_3d.c:45); coarser ones are elided
+        StageTimer t(s, timed && q == s->L - 1, q, MGB_ST_RESID2);
+        if (q == s->L - 1)
+            q_residual(s, q, false, 0);
+    }
+}
+
+static int build_graph(mgb_solver *s)
+{
+    cudaGraph_t graph = nullptr;
+    std::vector<int> saved = s->calls;
+    const long long before = launches_issued();
+    CK(cudaStreamBeginCapture(s->st, cudaStreamCaptureModeThreadLocal));
+    enqueue_cycle(s, s->L - 1, false);
+    cudaError_t e = cudaStreamEndCapture(s->st, &graph);
+    s->calls = saved;  // capture is not a cycle
+    s->graph_launches = launches_issued() - before;
+    if (e != cudaSuccess)
+        return fail("graph capture failed: %s", cudaGetErrorString(e));
+    e = cudaGraphInstantiate(&s->gexec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (e != cudaSuccess) {
+        s->gexec = nullptr;
+        return fail("graph instantiate failed: %s", cudaGetErrorString(e));
+    }
+    return 0;
+}
+
+static void bump_calls_like_cycle(mgb_solver *s)
+{
+    for (int q = s->L - 1; q >= 1; q--) {
+        int *c = &s->calls[(size_t)q * MGB_NUM_STAGES];
+        c[MGB_ST_SMOOTH1]++; c[MGB_ST_RESID1]++; c[MGB_ST_RESTRICT]++;
+        c[MGB_ST_RECURSE]++; c[MGB_ST_PROLONG]++; c[MGB_ST_SMOOTH2]++;
+        c[MGB_ST_RESID2]++;
+    }
+    s->calls[MGB_ST_RECURSE]++;
+}
+
+extern "C" int mgb_vcycle(mgb_solver *s, double *sumsq)
+{
+    if (bind(s))
+        return 1;
+    if (s->L > 1 && !s->lu)
+        return fail("no coarse operator");
+    if (s->L < 2)
+        return fail("a V-cycle needs at least 2 levels");
+    if (s->opt_profile) {
+        // eager launches bracketed by CUDA events per level and stage
+        const long long before = launches_issued();
+        s->ev_used = 0;
+        s->marks.clear();
+        enqueue_cycle(s, s->L - 1, true);
+        s->launches += launches_issued() - before;
+        CKLAUNCH();
+        double v;
+        if (fetch_scalar(s, 0, &v))
+            return 1;
+        for (auto &m : s->marks) {
+            float ms = 0.f;
+            CK(cudaEventElapsedTime(&ms, m.a, m.b));
+            s->secs[(size_t)m.level * MGB_NUM_STAGES + m.stage] += 1e-3 * ms;
+        }
+        if (sumsq)
+            *sumsq = v;
+        return 0;
+    }
+    if (s->opt_graph) {
+        if (!s->gexec && build_graph(s))
+            return 1;
+        CK(cudaGraphLaunch(s->gexec, s->st));
+        s->launches += s->graph_launches;
+    } else {
+        const long long before = launches_issued();
+        std::vector<int> saved = s->calls;
+        enqueue_cycle(s, s->L - 1, false);
+        s->calls = saved;
+        s->launches += launches_issued() - before;
+        CKLAUNCH();
+    }
+    bump_calls_like_cycle(s);
+    double v;
+    if (fetch_scalar(s, 0, &v))
+        return 1;
+    if (sumsq)
+        *sumsq = v;
+    return 0;
+}
+
+extern "C" int mgb_solve(mgb_solver *s, double threshold, int max_cycles,
+                         double *history, int *cycles)
+{
+    // test_mg_3d.c:40-66
+    double norm = 1e9;
+    int c = 0;
+    while (norm > threshold && c < max_cycles) {
+        double ss;
+        if (mgb_vcycle(s, &ss))
+            return 1;
+        norm = sqrt(ss);
+        if (history)
+            history[c] = norm;
+        c++;
+    }
+    if (cycles)
+        *cycles = c;
+    return 0;
+}
+
+extern "C" int mgb_timing(mgb_solver *s, int level, int stage, int *calls, double *seconds)
+{
+    if (!s)
+        return fail("null solver");
+    if (level < 0 || level >= s->L || stage < 0 || stage >= MGB_NUM_STAGES)
+        return fail("level/stage out of range");
+    if (calls)
+        *calls = s->calls[(size_t)level * MGB_NUM_STAGES + stage];
+    if (seconds)
+        *seconds = s->secs[(size_t)level * MGB_NUM_STAGES + stage];
+    return 0;
+}
+
+extern "C" int mgb_timing_reset(mgb_solver *s)
+{
+    if (!s)
+        return fail("null solver");
+    std::fill(s->secs.begin(), s->secs.end(), 0.);
+    std::fill(s->calls.begin(), s->calls.end(), 0);
+    return 0;
+}
+
+extern "C" long long mgb_launch_count(const mgb_solver *s) { return s ? s->launches : 0; }
+
+// ----------------------------------------------------------------------------
+// stateless host-array entry points (raw-pointer API of the reference)
+// ----------------------------------------------------------------------------
+namespace {
+
+struct Tmp {
+    Geo g;
+    DevArray a;
+    ~Tmp() { dev_free(&a); }
+};
+
+struct Scratch {
+    double *p = nullptr;
+    ~Scratch()
+    {
+        if (p)
+            cudaFree(p);
+    }
+};
+
+int host_ready()
+{
+    int n = 0;
+    if (mgb_device_count(&n))
+        return 1;
+    if (n < 1)
+        return fail("no CUDA device: libmgb has no CPU fallback");
+    return 0;
+}
+
+int tmp_make(Tmp *t, int ni, int nj, int nk)
+{
+    if (ni < 3 || nj < 3 || nk < 3)
+        return fail("extents must be >= 3");
+    t->g = make_geo(ni, nj, nk, ni, 0);
+    return dev_alloc(t->g, &t->a);
+}
+
+int tmp_upload(Tmp *t, const double *host, double *stage)
+{
+    const size_t n = (size_t)t->g.ni * t->g.nj * t->g.nk;
+    CK(cudaMemcpy(stage, host, sizeof(double) * n, cudaMemcpyHostToDevice));
+    launch_pack(t->g, stage, t->a.base, 0);
+    CKLAUNCH();
+    CK(cudaDeviceSynchronize());
+    return 0;
+}
+
+int tmp_download(Tmp *t, double *host, double *stage)
+{
+    const size_t n = (size_t)t->g.ni * t->g.nj * t->g.nk;
+    launch_unpack(t->g, t->a.base, stage, 0);
+    CKLAUNCH();
+    CK(cudaMemcpy(host, stage, sizeof(double) * n, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+}  // namespace
+
+extern "C" int mgb_host_smooth(double *v, const double *d, int ni, int nj, int nk,
+                               double h, int iters, int first_red)
+{
+    if (host_ready())
+        return 1;
+    Tmp tv, td;
+    Scratch st;
+    if (tmp_make(&tv, ni, nj, nk) || tmp_make(&td, ni, nj, nk))
+        return 1;
+    CK(cudaMalloc(&st.p, sizeof(double) * (size_t)ni * nj * nk));
+    if (tmp_upload(&tv, v, st.p) || tmp_upload(&td, d, st.p))
+        return 1;
+    const double hSq = h * h;
+    for (int it = 0; it < iters; it++) {
+        launch_half_sweep(tv.g, tv.a.base, td.a.base, hSq, first_red ? 1 : 0, 1, ni - 1, 0);
+        launch_half_sweep(tv.g, tv.a.base, td.a.base, hSq, first_red ? 0 : 1, 1, ni - 1, 0);
+    }
+    CKLAUNCH();
+    return tmp_download(&tv, v, st.p);
+}
+
+extern "C" int mgb_host_residual(const double *v, const double *d, int ni, int nj,
+                                 int nk, double h, double *res, double *sumsq)
+{
+    if (host_ready())
+        return 1;
+    Tmp tv, td, tr;
+    Scratch st, sc;
+    if (tmp_make(&tv, ni, nj, nk) || tmp_make(&td, ni, nj, nk))
+        return 1;
+    if (res && tmp_make(&tr, ni, nj, nk))
+        return 1;
+    CK(cudaMalloc(&st.p, sizeof(double) * (size_t)ni * nj * nk));
+    CK(cudaMalloc(&sc.p, sizeof(double) * (kMaxPartials + 1)));
+    if (tmp_upload(&tv, v, st.p) || tmp_upload(&td, d, st.p))
+        return 1;
+    // res keeps its previous boundary values (the reference only writes the
+    // interior, mg_3d.h:807-826)
+    if (res && tmp_upload(&tr, res, st.p))
+        return 1;
+    launch_residual(tv.g, tv.a.base, td.a.base, res ? tr.a.base : nullptr, 1. / (h * h), 1,
+                    ni - 1, sc.p + 1, sc.p, 0);
+    CKLAUNCH();
+    double ss = 0.;
+    CK(cudaMemcpy(&ss, sc.p, sizeof(double), cudaMemcpyDeviceToHost));
+    if (sumsq)
+        *sumsq = ss;
+    if (res)
+        return tmp_download(&tr, res, st.p);
+    return 0;
+}
+
+extern "C" int mgb_host_restrict(const double *r, int nif, int njf, int nkf, double *dc,
+                                 int nic, int njc, int nkc)
+{
+    if (host_ready())
+        return 1;
+    if (nif != 2 * nic - 1 || njf != 2 * njc - 1 || nkf != 2 * nkc - 1)
+        return fail("fine extents must be 2*coarse-1");
+    Tmp tf, tc;
+    Scratch st;
+    if (tmp_make(&tf, nif, njf, nkf) || tmp_make(&tc, nic, njc, nkc))
+        return 1;
+    CK(cudaMalloc(&st.p, sizeof(double) * (size_t)nif * njf * nkf));
+    if (tmp_upload(&tf, r, st.p))
+        return 1;
+    launch_restrict(tf.g, tf.a.base, tc.g, tc.a.base, 0, nic, 0);
+    CKLAUNCH();
+    return tmp_download(&tc, dc, st.p);
+}
+
+extern "C" int mgb_host_prolong_correct(const double *ec, int nic, int njc, int nkc,
+                                        double *ef, int nif, int njf, int nkf)
+{
+    if (host_ready())
+        return 1;
+    if (nif != 2 * nic - 1 || njf != 2 * njc - 1 || nkf != 2 * nkc - 1)
+        return fail("fine extents must be 2*coarse-1");
+    Tmp tf, tc;
+    Scratch st;
+    if (tmp_make(&tf, nif, njf, nkf) || tmp_make(&tc, nic, njc, nkc))
+        return 1;
+    CK(cudaMalloc(&st.p, sizeof(double) * (size_t)nif * njf * nkf));
+    if (tmp_upload(&tf, ef, st.p) || tmp_upload(&tc, ec, st.p))
+        return 1;
+    launch_prolong_correct(tc.g, tc.a.base, tf.g, tf.a.base, 0, nif, 0);
+    CKLAUNCH();
+    return tmp_download(&tf, ef, st.p);
+}
+
+extern "C" int mgb_host_coarse_matrix(double *A, int ni, int nj, int nk, double h)
+{
+    if (host_ready())
+        return 1;
+    const size_t n = (size_t)ni * nj * nk;
+    Scratch a;
+    CK(cudaMalloc(&a.p, sizeof(double) * n * n));
+    launch_coarse_matrix(a.p, ni, nj, nk, h, 0);
+    CKLAUNCH();
+    CK(cudaMemcpy(A, a.p, sizeof(double) * n * n, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+extern "C" int mgb_host_lu_factor(double *a, int n)
+{
+    if (host_ready())
+        return 1;
+    Scratch d;
+    CK(cudaMalloc(&d.p, sizeof(double) * (size_t)n * n));
+    CK(cudaMemcpy(d.p, a, sizeof(double) * (size_t)n * n, cudaMemcpyHostToDevice));
+    launch_lu_factor(d.p, n, 0);
+    CKLAUNCH();
+    CK(cudaMemcpy(a, d.p, sizeof(double) * (size_t)n * n, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+extern "C" int mgb_host_lu_solve(const double *lu, int n, const double *b, double *x)
+{
+    if (host_ready())
+        return 1;
+    if (n > MGB_MAX_DENSE_N)
+        return fail("n=%d exceeds MGB_MAX_DENSE_N", n);
+    Scratch d, t, vb, vx;
+    CK(cudaMalloc(&d.p, sizeof(double) * (size_t)n * n));
+    CK(cudaMalloc(&t.p, sizeof(double) * (size_t)n * n));
+    CK(cudaMalloc(&vb.p, sizeof(double) * n));
+    CK(cudaMalloc(&vx.p, sizeof(double) * n));
+    CK(cudaMemcpy(d.p, lu, sizeof(double) * (size_t)n * n, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(vb.p, b, sizeof(double) * n, cudaMemcpyHostToDevice));
+    launch_transpose(d.p, t.p, n, 0);
+    launch_lu_solve(d.p, t.p, n, vb.p, vx.p, 0);
+    CKLAUNCH();
+    CK(cudaMemcpy(x, vx.p, sizeof(double) * n, cudaMemcpyDeviceToHost));
+    return 0;
+}

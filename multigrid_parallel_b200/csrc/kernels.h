@@ -1,0 +1,58 @@
+// kernels.h -- launch wrappers of the sm_100a kernels (host-callable, C++).
+#pragma once
+#include <cuda_runtime.h>
+
+#include "geom.h"
+
+namespace mgb {
+
+// number of partial sums a residual / sumsq launch may produce
+constexpr int kMaxPartials = 1 << 16;
+
+// natural <-> colour-split (API boundary only)
+void launch_pack(const Geo &g, const double *nat, double *split, cudaStream_t st);
+void launch_unpack(const Geo &g, const double *split, double *nat, cudaStream_t st);
+
+// Dirichlet faces: analytic BCFunc (mg_3d.h:89-90, 1147-1239)
+void launch_set_dirichlet(const Geo &g, double *a, double h, cudaStream_t st);
+
+// one colour of the RB-GS smoother over local planes [il_lo, il_hi)
+// (mg_3d.h:432-443, 658-702)
+void launch_half_sweep(const Geo &g, double *v, const double *d, double hSq,
+                       int colour, int il_lo, int il_hi, cudaStream_t st);
+
+// residual (mg_3d.h:794-842) over local planes [il_lo, il_hi); r may be
+// nullptr; the sum of squares lands in *out_sumsq (device) via `partials`
+void launch_residual(const Geo &g, const double *v, const double *d, double *r,
+                     double invHsq, int il_lo, int il_hi, double *partials,
+                     double *out_sumsq, cudaStream_t st);
+
+// full-weighting restriction r(fine) -> d(coarse) (mg_3d.h:844-998) for local
+// coarse planes [Il_lo, Il_hi)
+void launch_restrict(const Geo &gf, const double *rf, const Geo &gc, double *dc,
+                     int Il_lo, int Il_hi, cudaStream_t st);
+
+// trilinear prolongation + correction (mg_3d.h:1000-1145) for local fine
+// planes [il_lo, il_hi)
+void launch_prolong_correct(const Geo &gc, const double *ec, const Geo &gf,
+                            double *ef, int il_lo, int il_hi, cudaStream_t st);
+
+// sum of squares of every stored entry (pads are zero) -> *out (device)
+void launch_sumsq(const double *a, long long n, double *partials, double *out,
+                  cudaStream_t st);
+// sum over all points of (u - BCFunc(ih,jh,kh))^2 (test_mg_3d.c:78-97)
+void launch_error_sumsq(const Geo &g, const double *u, double h,
+                        double *partials, double *out, cudaStream_t st);
+
+// dense coarse operator + LU (mg_3d.h:147-273, gauss_elim.h:9-60)
+void launch_coarse_matrix(double *A, int ni, int nj, int nk, double h,
+                          cudaStream_t st);
+void launch_lu_factor(double *a, int n, cudaStream_t st);
+void launch_transpose(const double *a, double *at, int n, cudaStream_t st);
+// x = (LU)^-1 b; lut = transpose of lu; b, x are plain dense vectors
+void launch_lu_solve(const double *lu, const double *lut, int n, const double *b,
+                     double *x, cudaStream_t st);
+// launches issued through the wrappers above (all threads, all solvers)
+long long launches_issued();
+
+}  // namespace mgb

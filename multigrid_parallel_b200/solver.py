@@ -1,0 +1,208 @@
+"""Python mirror of the C ABI (include/mgb.h): a handle class + array helpers.
+
+Everything here forwards to libmgb.so; arrays cross the boundary as float64
+numpy arrays in the reference's natural layout (shape (ni, nj, nk), C order).
+"""
+import ctypes as C
+import math
+
+import numpy as np
+
+from ._lib import c_dp, check, load_library
+
+MGB_U, MGB_D, MGB_R = 0, 1, 2
+OPT_GRAPH, OPT_PROFILE, OPT_FUSE = 0, 1, 2
+# mg_3d.h:136-137
+STAGE_NAMES = ("Smoother1", "CalcResidual1", "Restrict Residual", "Recurse, Direct Solve",
+               "Prolongate&Correct", "Smoother2", "CalcResidual2")
+
+
+def _dp(a):
+    assert a.dtype == np.float64 and a.flags["C_CONTIGUOUS"], "need C-contiguous float64"
+    return a.ctypes.data_as(c_dp)
+
+
+class Solver:
+    """One multigrid hierarchy on one GPU (mgb_create ... mgb_destroy).
+
+    Mirrors the reference's solver state (mg_3d.h:19-28): `coarse` points per
+    side on level 0, `levels` grids, `gs` smoothing iterations per leg.
+    """
+
+    def __init__(self, coarse, levels, gs, device=0):
+        self.L = load_library()
+        if isinstance(coarse, int):
+            coarse = (coarse,) * 3
+        self.h_ = C.c_void_p()
+        check(self.L.mgb_create(C.byref(self.h_), *coarse, levels, gs, device))
+        self.levels = levels
+        self.gs = gs
+
+    # -- lifecycle ---------------------------------------------------------
+    def close(self):
+        if getattr(self, "h_", None) is not None and self.h_:
+            self.L.mgb_destroy(self.h_)
+            self.h_ = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    # -- geometry ----------------------------------------------------------
+    def dims(self, level=None):
+        level = self.levels - 1 if level is None else level
+        a, b, c = C.c_int(), C.c_int(), C.c_int()
+        check(self.L.mgb_dims(self.h_, level, a, b, c))
+        return a.value, b.value, c.value
+
+    def spacing(self, level=None):
+        level = self.levels - 1 if level is None else level
+        return self.L.mgb_spacing(self.h_, level)
+
+    def set_option(self, key, value):
+        check(self.L.mgb_set_option(self.h_, key, int(value)))
+
+    def sync(self):
+        check(self.L.mgb_sync(self.h_))
+
+    # -- arrays ------------------------------------------------------------
+    def upload(self, level, which, host):
+        host = np.ascontiguousarray(host, dtype=np.float64)
+        assert host.shape == self.dims(level), (host.shape, self.dims(level))
+        check(self.L.mgb_upload(self.h_, level, which, host.ctypes.data))
+
+    def upload_ptr(self, level, which, ptr):
+        check(self.L.mgb_upload(self.h_, level, which, ptr))
+
+    def download(self, level, which, out=None):
+        if out is None:
+            out = np.empty(self.dims(level), dtype=np.float64)
+        check(self.L.mgb_download(self.h_, level, which, out.ctypes.data))
+        return out
+
+    def download_ptr(self, level, which, ptr):
+        check(self.L.mgb_download(self.h_, level, which, ptr))
+
+    def zero(self, level, which):
+        check(self.L.mgb_zero(self.h_, level, which))
+
+    def set_dirichlet(self, level, which):
+        check(self.L.mgb_set_dirichlet(self.h_, level, which))
+
+    def sumsq(self, level, which):
+        v = C.c_double()
+        check(self.L.mgb_sumsq(self.h_, level, which, v))
+        return v.value
+
+    def error_sumsq(self):
+        v = C.c_double()
+        check(self.L.mgb_error_sumsq(self.h_, v))
+        return v.value
+
+    # -- operators ---------------------------------------------------------
+    def half_sweep(self, level, colour):
+        check(self.L.mgb_half_sweep(self.h_, level, colour))
+
+    def smooth(self, level, iters, first_red):
+        check(self.L.mgb_smooth(self.h_, level, iters, int(first_red)))
+
+    def residual(self, level, store_r=False):
+        """returns sqrt(sum of squares) like calculateResidual on one thread"""
+        v = C.c_double()
+        check(self.L.mgb_residual(self.h_, level, int(store_r), v))
+        return math.sqrt(v.value)
+
+    def restrict(self, level):
+        check(self.L.mgb_restrict(self.h_, level))
+
+    def residual_restrict(self, level):
+        check(self.L.mgb_residual_restrict(self.h_, level))
+
+    def prolong_correct(self, level):
+        check(self.L.mgb_prolong_correct(self.h_, level))
+
+    def coarse_solve(self):
+        check(self.L.mgb_coarse_solve(self.h_))
+
+    def coarse_lu(self):
+        n = int(np.prod(self.dims(0)))
+        a = np.empty((n, n))
+        check(self.L.mgb_coarse_lu_download(self.h_, a.ctypes.data))
+        return a
+
+    # -- cycles ------------------------------------------------------------
+    def vcycle(self):
+        """one V-cycle; returns the residual 2-norm (SolverLinSolve)"""
+        v = C.c_double()
+        check(self.L.mgb_vcycle(self.h_, v))
+        return math.sqrt(v.value)
+
+    def solve(self, threshold, max_cycles=100):
+        hist = np.zeros(max_cycles)
+        n = C.c_int()
+        check(self.L.mgb_solve(self.h_, threshold, max_cycles, _dp(hist), n))
+        return hist[: n.value].copy()
+
+    def timing(self, level, stage):
+        c, s = C.c_int(), C.c_double()
+        check(self.L.mgb_timing(self.h_, level, stage, c, s))
+        return c.value, s.value
+
+    def timing_reset(self):
+        check(self.L.mgb_timing_reset(self.h_))
+
+    @property
+    def launch_count(self):
+        return self.L.mgb_launch_count(self.h_)
+
+
+# ---- stateless array entry points (the reference's raw-pointer API) -------
+def host_smooth(v, d, h, iters, first_red):
+    L = load_library()
+    check(L.mgb_host_smooth(_dp(v), _dp(d), *v.shape, h, iters, int(first_red)))
+
+
+def host_residual(v, d, h, res=None):
+    L = load_library()
+    ss = C.c_double()
+    check(L.mgb_host_residual(_dp(v), _dp(d), *v.shape, h,
+                              _dp(res) if res is not None else None, ss))
+    return math.sqrt(ss.value)
+
+
+def host_restrict(r, dc):
+    L = load_library()
+    check(L.mgb_host_restrict(_dp(r), *r.shape, _dp(dc), *dc.shape))
+
+
+def host_prolong_correct(ec, ef):
+    L = load_library()
+    check(L.mgb_host_prolong_correct(_dp(ec), *ec.shape, _dp(ef), *ef.shape))
+
+
+def host_coarse_matrix(shape, h):
+    L = load_library()
+    n = int(np.prod(shape))
+    A = np.zeros((n, n))
+    check(L.mgb_host_coarse_matrix(_dp(A), *shape, h))
+    return A
+
+
+def host_lu_factor(a):
+    L = load_library()
+    check(L.mgb_host_lu_factor(_dp(a), a.shape[0]))
+
+
+def host_lu_solve(lu, b):
+    L = load_library()
+    x = np.zeros_like(b)
+    check(L.mgb_host_lu_solve(_dp(lu), lu.shape[0], _dp(b), _dp(x)))
+    return x
