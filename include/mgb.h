@@ -117,6 +117,13 @@ int mgb_timing(mgb_solver *s, int level, int stage, int *calls, double *seconds)
 int mgb_timing_reset(mgb_solver *s);
 /* number of kernel launches (graph nodes included) issued since creation */
 long long mgb_launch_count(const mgb_solver *s);
+/* CUDA-event stopwatch on the solver's own stream (the stream every kernel of
+ * this solver is launched on): start records an event, stop records a second
+ * one, waits for it and returns the device time between them */
+int mgb_timer_start(mgb_solver *s);
+int mgb_timer_stop(mgb_solver *s, double *seconds);
+/* the solver's cudaStream_t (for interop, e.g. torch.cuda.ExternalStream) */
+void *mgb_stream(mgb_solver *s);
 
 /* ---- stateless array entry points for the reference's raw-pointer API
  * (test_rb_gs_3d.c:70-81 and test_lu.c:33-42 call these on caller-owned host

@@ -75,6 +75,10 @@ def load_library():
     L.mgb_timing_reset.argtypes = [vp]
     L.mgb_launch_count.restype = C.c_longlong
     L.mgb_launch_count.argtypes = [vp]
+    L.mgb_timer_start.argtypes = [vp]
+    L.mgb_timer_stop.argtypes = [vp, c_dp]
+    L.mgb_stream.restype = C.c_void_p
+    L.mgb_stream.argtypes = [vp]
     L.mgb_host_smooth.argtypes = [c_dp, c_dp, i, i, i, d, i, i]
     L.mgb_host_residual.argtypes = [c_dp, c_dp, i, i, i, d, c_dp, c_dp]
     L.mgb_host_restrict.argtypes = [c_dp, i, i, i, c_dp, i, i, i]

@@ -127,6 +127,7 @@ struct mgb_solver {
     std::vector<cudaEvent_t> ev_pool;
     size_t ev_used = 0;
     std::vector<StageMark> marks;
+    cudaEvent_t sw_a = nullptr, sw_b = nullptr;  // stopwatch
 };
 
 struct LaunchScope {
@@ -170,6 +171,8 @@ extern "C" int mgb_destroy(mgb_solver *s)
             dev_free(&l.a[w]);
     for (auto e : s->ev_pool)
         cudaEventDestroy(e);
+    if (s->sw_a) cudaEventDestroy(s->sw_a);
+    if (s->sw_b) cudaEventDestroy(s->sw_b);
     if (s->partials) cudaFree(s->partials);
     if (s->d_scal) cudaFree(s->d_scal);
     if (s->h_scal) cudaFreeHost(s->h_scal);
@@ -796,6 +799,35 @@ extern "C" int mgb_timing_reset(mgb_solver *s)
 }
 
 extern "C" long long mgb_launch_count(const mgb_solver *s) { return s ? s->launches : 0; }
+
+extern "C" int mgb_timer_start(mgb_solver *s)
+{
+    if (bind(s))
+        return 1;
+    if (!s->sw_a) {
+        CK(cudaEventCreate(&s->sw_a));
+        CK(cudaEventCreate(&s->sw_b));
+    }
+    CK(cudaEventRecord(s->sw_a, s->st));
+    return 0;
+}
+
+extern "C" int mgb_timer_stop(mgb_solver *s, double *seconds)
+{
+    if (bind(s))
+        return 1;
+    if (!s->sw_a)
+        return fail("mgb_timer_stop without mgb_timer_start");
+    CK(cudaEventRecord(s->sw_b, s->st));
+    CK(cudaEventSynchronize(s->sw_b));
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, s->sw_a, s->sw_b));
+    if (seconds)
+        *seconds = 1e-3 * (double)ms;
+    return 0;
+}
+
+extern "C" void *mgb_stream(mgb_solver *s) { return s ? (void *)s->st : nullptr; }
 
 // ----------------------------------------------------------------------------
 // stateless host-array entry points (raw-pointer API of the reference)

@@ -159,6 +159,15 @@ class Solver:
     def timing_reset(self):
         check(self.L.mgb_timing_reset(self.h_))
 
+    def timer_start(self):
+        check(self.L.mgb_timer_start(self.h_))
+
+    def timer_stop(self):
+        """device seconds since timer_start (CUDA events on the solver's stream)"""
+        v = C.c_double()
+        check(self.L.mgb_timer_stop(self.h_, v))
+        return v.value
+
     @property
     def launch_count(self):
         return self.L.mgb_launch_count(self.h_)
