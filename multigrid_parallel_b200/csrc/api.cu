@@ -483,9 +483,9 @@ static void q_restrict(mgb_solver *s, int q)
 
 static void q_residual_restrict(mgb_solver *s, int q)
 {
-    // single-pass fused kernel not in yet: residual into r, then restrict
-    q_residual(s, q, true, 3);
-    q_restrict(s, q);
+    Level &f = s->lv[q], &c = s->lv[q - 1];
+    launch_residual_restrict(f.g, f.a[MGB_U].base, f.a[MGB_D].base, f.invHsq, c.g,
+                             c.a[MGB_D].base, 0, c.g.li, s->st);
 }
 
 static void q_prolong(mgb_solver *s, int q)

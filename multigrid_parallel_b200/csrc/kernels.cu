@@ -8,6 +8,7 @@
 // Every stage is HBM-bound (0.3 flop/B); no tensor cores on purpose.
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 
 #include "kernels.h"
 
@@ -211,19 +212,54 @@ struct MarchCfg {
     int chunk;
 };
 
+// number of plane chunks (grid.y) when one chunk is bx blocks and `resident`
+// blocks fit on an SM.  Small grids: one plane per thread (all the parallelism
+// there is; they are latency-bound).  Large grids: chunks of >= 8 planes (the
+// i-1/i planes are re-read at every chunk start) and a block count that ends
+// close to a whole number of waves over the 148 SMs.
+static int pick_chunks(long long bx, int nplanes, int resident)
+{
+    const long long cap = 148LL * resident;
+    if (bx * nplanes <= 3 * cap || nplanes < 16)
+        return nplanes;
+    int best = 1;
+    double best_score = -1.;
+    const int max_by = nplanes / 8;
+    for (int by = 1; by <= max_by; by++) {
+        const int chunk = (nplanes + by - 1) / by;
+        const int real_by = (nplanes + chunk - 1) / chunk;
+        const long long total = bx * real_by;
+        if (total < 2 * cap && by < max_by)
+            continue;  // want at least two waves
+        const long long waves = (total + cap - 1) / cap;
+        double eff = (double)total / (double)(waves * cap);  // tail efficiency
+        eff *= (double)chunk / (chunk + 2.0);                // chunk start-up cost
+        if (eff > best_score + 1e-9) {
+            best_score = eff;
+            best = real_by;
+        }
+    }
+    return best;
+}
+
+// resident blocks per SM of a kernel, from the occupancy calculator (cached)
+template <typename K>
+static int resident_blocks(K kernel, int threads, size_t smem)
+{
+    int n = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, threads, smem) != cudaSuccess ||
+        n < 1)
+        n = 1;
+    return n;
+}
+
 static MarchCfg march_cfg(const Geo &g, int nplanes, int threads, int sm_blocks)
 {
     MarchCfg c;
     const long long pairs = (long long)g.pj / 2;
     const unsigned bx = (unsigned)((pairs + threads - 1) / threads);
-    // aim at ~2 waves of resident blocks over the 148 SMs
-    long long want = 2LL * 148 * sm_blocks;
-    long long nch = (want + bx - 1) / bx;
-    if (nch < 1)
-        nch = 1;
-    if (nch > nplanes)
-        nch = nplanes;
-    c.chunk = (int)((nplanes + nch - 1) / nch);
+    const int nch = pick_chunks(bx, nplanes, sm_blocks);
+    c.chunk = (nplanes + nch - 1) / nch;
     const unsigned by = (unsigned)((nplanes + c.chunk - 1) / c.chunk);
     c.grid = dim3(bx, by, 1);
     c.block = dim3(threads, 1, 1);
@@ -298,7 +334,8 @@ void launch_half_sweep(const Geo &g, double *v, const double *d, double hSq,
 {
     if (il_hi <= il_lo)
         return;
-    const MarchCfg c = march_cfg(g, il_hi - il_lo, 256, 8);
+    static const int occ = resident_blocks(k_half_sweep<1>, 256, 0);
+    const MarchCfg c = march_cfg(g, il_hi - il_lo, 256, occ);
     if (colour)
         k_half_sweep<1><<<c.grid, c.block, 0, st>>>(g, v, v + g.cs, d + g.cs, hSq,
                                                     il_lo, il_hi, c.chunk);
@@ -389,7 +426,8 @@ void launch_residual(const Geo &g, const double *v, const double *d, double *r,
         cudaMemsetAsync(out_sumsq, 0, sizeof(double), st);
         return;
     }
-    MarchCfg c = march_cfg(g, il_hi - il_lo, 256, 4);
+    static const int occ = resident_blocks(k_residual<true>, 256, 0);
+    MarchCfg c = march_cfg(g, il_hi - il_lo, 256, occ);
     while ((long long)c.grid.x * c.grid.y > kMaxPartials) {  // coarser chunks
         c.chunk *= 2;
         c.grid.y = (il_hi - il_lo + c.chunk - 1) / c.chunk;
@@ -460,69 +498,346 @@ void launch_restrict(const Geo &gf, const double *rf, const Geo &gc, double *dc,
 }
 
 // ----------------------------------------------------------------------------
-// prolongation + correction (mg_3d.h:1000-1145): one thread per fine entry
+// fused residual + full-weighting restriction (mg_3d.h:794-842 + 844-998)
+//
+// The fine residual is never written to HBM (17 B/DOF instead of 24 + 9).
+// A block owns TY coarse rows (all K) and marches over fine planes.  Per fine
+// plane f every thread computes the residual of its four fine points
+// (row j, k = 4mp..4mp+3, both colours; i-neighbours carried in registers like
+// k_residual) and drops them into a shared plane buffer in natural k order;
+// after one barrier the threads sitting on even fine rows (j = 2J) add the
+// 3x3 neighbourhood of that plane into the accumulators of their two coarse
+// points (J, 2mp) and (J, 2mp+1).  A coarse value is the sum over the planes
+// 2I-1, 2I, 2I+1 in that order, nine terms each in (tj,tk) order, starting from
+// 0. -- exactly the (ti,tj,tk) loop nest of mg_3d.h:980-989 -- so an odd plane
+// closes coarse plane I and opens I+1 with the same nine products.
+// The block covers fine rows 2Ja-1 .. 2(Ja+TY)-1: one odd row is recomputed by
+// the neighbouring block (1/(2TY+1) redundancy, L2 hits).
+// Boundary coarse entries are the injected boundary residual, which is 0
+// (mg_3d.h:881-957 with r's faces never written).
 // ----------------------------------------------------------------------------
+template <int MAXT>
+__global__ void __launch_bounds__(MAXT)
+k_residual_restrict(Geo gf, const double *__restrict__ v, const double *__restrict__ d,
+                    double invHsq, Geo gc, double *__restrict__ dc, int Il_lo, int Il_hi,
+                    int chunk, int TY)
+{
+    extern __shared__ double rs_all[];
+    const int npair = gf.kh >> 1;
+    const int R = 2 * TY + 1;
+    const int SP = 4 * npair + 2;  // row pitch; data starts at +2 (k = -1 lands on +1)
+    const int t = threadIdx.x;
+    const int jl = t / npair;
+    const int mp = t - jl * npair;
+    const bool active = jl < R;
+    const int Ja = blockIdx.x * TY;
+    const int j = 2 * Ja - 1 + jl;
+    const bool row_in = active && j >= 1 && j <= gf.nj - 2;  // interior fine row
+    // coarse role: even fine rows j = 2J
+    const int J = Ja + ((jl - 1) >> 1);
+    const bool coarse_thr = active && (jl & 1) && jl <= R - 2 && J < gc.nj;
+    const int K0 = 2 * mp, K1 = 2 * mp + 1;
+    const bool K0in = K0 < gc.nk, K1in = K1 < gc.nk;
+    const bool Jint = J >= 1 && J <= gc.nj - 2;
+    const bool K0int = Jint && K0 >= 1 && K0 <= gc.nk - 2;
+    const bool K1int = Jint && K1 >= 1 && K1 <= gc.nk - 2;
+
+    const int Ia = Il_lo + blockIdx.y * chunk;
+    const int Ib = min(Ia + chunk, Il_hi);
+    // interior coarse planes of this chunk (global index 1 .. ni-2)
+    const int Im0 = max(Ia, 1 - gc.i0);
+    const int Im1 = min(Ib, gc.ni - 1 - gc.i0);
+
+    // coarse boundary planes inside the chunk: zeros
+    if (coarse_thr) {
+        for (int Il = Ia; Il < Ib; Il++) {
+            const int Ig = gc.i0 + Il;
+            if (Ig != 0 && Ig != gc.ni - 1)
+                continue;
+            const int S = (Ig + J) & 1;
+            const long long row = ((long long)Il * gc.nj + J) * gc.kh;
+            if (K0in) dc[(long long)S * gc.cs + row + mp] = 0.;
+            if (K1in) dc[(long long)(S ^ 1) * gc.cs + row + mp] = 0.;
+        }
+    }
+    if (Im0 >= Im1)
+        return;
+
+    const int f0 = 2 * (gc.i0 + Im0) - 1 - gf.i0;      // first fine local plane
+    const int f1 = 2 * (gc.i0 + Im1 - 1) + 1 - gf.i0;  // last fine local plane
+    const long long off = ((long long)j * npair + mp) * 2;
+    const int kh = gf.kh;
+    const int kmax = gf.nk - 2;
+    const double *p0 = v + (long long)f0 * gf.pj + off;
+    const double *p1 = p0 + gf.cs;
+    double2 bot0, mid0, bot1, mid1;
+    bot0 = mid0 = bot1 = mid1 = make_double2(0., 0.);
+    if (row_in) {
+        bot0 = ld2(p0 - gf.pj); mid0 = ld2(p0);
+        bot1 = ld2(p1 - gf.pj); mid1 = ld2(p1);
+    }
+    double acc0 = 0., acc1 = 0.;
+    bool have_cur = false;
+    int buf = 0;
+    for (int il = f0; il <= f1; il++, p0 += gf.pj, p1 += gf.pj) {
+        double *rs = rs_all + (size_t)buf * R * SP;
+        const int ig = gf.i0 + il;
+        if (active) {
+            double n0 = 0., n1 = 0., n2 = 0., n3 = 0.;  // residuals at k = 4mp..4mp+3
+            if (row_in) {
+                const double2 top0 = ld2(p0 + gf.pj), top1 = ld2(p1 + gf.pj);
+                const double2 jm0 = ld2(p0 - kh), jp0 = ld2(p0 + kh);
+                const double2 jm1 = ld2(p1 - kh), jp1 = ld2(p1 + kh);
+                const long long idx = (long long)il * gf.pj + off;
+                const double2 d0 = ld2(d + idx), d1 = ld2(d + gf.cs + idx);
+                const int s = (ig + j) & 1;
+                double b0, b1, b2, c0, c1, c2;
+                if (s) {
+                    b0 = mid1.x; b1 = mid1.y; b2 = p1[2];
+                    c0 = p0[-1]; c1 = mid0.x; c2 = mid0.y;
+                } else {
+                    b0 = p1[-1]; b1 = mid1.x; b2 = mid1.y;
+                    c0 = mid0.x; c1 = mid0.y; c2 = p0[2];
+                }
+                double rb0 = res_point(bot1.x, top1.x, jm1.x, jp1.x, b0, b1, mid0.x, d0.x, invHsq);
+                double rb1 = res_point(bot1.y, top1.y, jm1.y, jp1.y, b1, b2, mid0.y, d0.y, invHsq);
+                double rr0 = res_point(bot0.x, top0.x, jm0.x, jp0.x, c0, c1, mid1.x, d1.x, invHsq);
+                double rr1 = res_point(bot0.y, top0.y, jm0.y, jp0.y, c1, c2, mid1.y, d1.y, invHsq);
+                const int kb0 = 4 * mp + s, kr0 = 4 * mp + (s ^ 1);
+                if (!(kb0 >= 1 && kb0 <= kmax)) rb0 = 0.;
+                if (!(kb0 + 2 <= kmax)) rb1 = 0.;
+                if (!(kr0 >= 1 && kr0 <= kmax)) rr0 = 0.;
+                if (!(kr0 + 2 <= kmax)) rr1 = 0.;
+                if (s) { n0 = rr0; n1 = rb0; n2 = rr1; n3 = rb1; }
+                else   { n0 = rb0; n1 = rr0; n2 = rb1; n3 = rr1; }
+                bot0 = mid0; mid0 = top0;
+                bot1 = mid1; mid1 = top1;
+            }
+            double *w = rs + (size_t)jl * SP + 2 + 4 * mp;
+            st2(w, n0, n1);
+            st2(w + 2, n2, n3);
+        }
+        __syncthreads();
+        if (coarse_thr) {
+            const bool odd = ig & 1;
+            const double wf = odd ? 0.5 : 1.0;  // ti = 0/2 vs ti = 1
+            const double *r0 = rs + (size_t)(jl - 1) * SP + 2 + 4 * mp - 1;
+            double s0 = 0., s1 = 0.;  // fresh sums (for the plane that opens I+1)
+            double a0 = acc0, a1 = acc1;
+#pragma unroll
+            for (int tj = 0; tj < 3; tj++) {
+                const double *rr = r0 + (size_t)tj * SP;
+                const double x0 = rr[0], x1 = rr[1], x2 = rr[2], x3 = rr[3], x4 = rr[4];
+                const double wc = (tj == 1 ? 0.125 : 0.0625) * wf;  // tk = 1
+                const double we = 0.5 * wc;                          // tk = 0, 2
+                const double p00 = __dmul_rn(x0, we), p01 = __dmul_rn(x1, wc),
+                             p02 = __dmul_rn(x2, we);
+                const double p10 = p02, p11 = __dmul_rn(x3, wc), p12 = __dmul_rn(x4, we);
+                a0 = __dadd_rn(__dadd_rn(__dadd_rn(a0, p00), p01), p02);
+                a1 = __dadd_rn(__dadd_rn(__dadd_rn(a1, p10), p11), p12);
+                s0 = __dadd_rn(__dadd_rn(__dadd_rn(s0, p00), p01), p02);
+                s1 = __dadd_rn(__dadd_rn(__dadd_rn(s1, p10), p11), p12);
+            }
+            if (odd) {
+                if (have_cur) {  // plane 2I+1 closes coarse plane I
+                    const int Il = ((ig - 1) >> 1) - gc.i0;
+                    const int S = (gc.i0 + Il + J) & 1;
+                    const long long row = ((long long)Il * gc.nj + J) * gc.kh;
+                    if (K0in) dc[(long long)S * gc.cs + row + mp] = K0int ? a0 : 0.;
+                    if (K1in) dc[(long long)(S ^ 1) * gc.cs + row + mp] = K1int ? a1 : 0.;
+                }
+                acc0 = s0;  // ... and opens I+1
+                acc1 = s1;
+                have_cur = true;
+            } else {
+                acc0 = a0;
+                acc1 = a1;
+            }
+        }
+        buf ^= 1;
+    }
+}
+
+void launch_residual_restrict(const Geo &gf, const double *vf, const double *df,
+                              double invHsq, const Geo &gc, double *dc, int Il_lo,
+                              int Il_hi, cudaStream_t st)
+{
+    if (Il_hi <= Il_lo)
+        return;
+    const int npair = gf.kh >> 1;
+    static const int maxt_env = getenv("MGB_RR_MAXT") ? atoi(getenv("MGB_RR_MAXT")) : 0;
+    const int maxt = maxt_env >= 96 && maxt_env <= 1024 ? maxt_env : 1024;
+    int R = maxt / npair;
+    if (R < 3) {
+        fprintf(stderr, "mgb: k_residual_restrict: rows of %d points are too long\n", gf.nk);
+        return;
+    }
+    if (!(R & 1))
+        R--;
+    int TY = (R - 1) / 2;
+    if (TY > gc.nj)
+        TY = gc.nj;
+    R = 2 * TY + 1;
+    const int threads = ((R * npair + 31) / 32) * 32;
+    const unsigned bx = (gc.nj + TY - 1) / TY;
+    const int nplanes = Il_hi - Il_lo;
+    const size_t sh = sizeof(double) * 2 * R * (4 * npair + 2);
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(k_residual_restrict<1024>,
+                             cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+        attr_set = true;
+    }
+    const int occ = resident_blocks(k_residual_restrict<1024>, threads, sh);
+    const int nch = pick_chunks(bx, nplanes, occ);
+    const int chunk = (nplanes + nch - 1) / nch;
+    const unsigned by = (nplanes + chunk - 1) / chunk;
+    k_residual_restrict<1024><<<dim3(bx, by), threads, sh, st>>>(gf, vf, df, invHsq, gc, dc,
+                                                               Il_lo, Il_hi, chunk, TY);
+    COUNT_LAUNCH();
+}
+
+// ----------------------------------------------------------------------------
+// prolongation + correction (mg_3d.h:1000-1145)
+//
+// A thread owns the four fine points k = 4mp..4mp+3 of fine row (i,j) -- the
+// pair (m, m+1) = (2mp, 2mp+1) of BOTH colours -- and marches over fine planes.
+// Everything it needs from the coarse grid is three consecutive entries
+// K = 2mp, 2mp+1, 2mp+2 of at most four coarse rows (I or I+1, J or J+1); the
+// two coarse planes are carried in registers, so each coarse row is fetched
+// once per two fine planes.  Fine traffic: one 128-bit load + store per colour.
+// The sums keep the reference's corner order and start from 0. (1018).
+// ----------------------------------------------------------------------------
+struct C3 {
+    double x, y, z;  // coarse entries K = 2mp, 2mp+1, 2mp+2
+};
+
+__device__ __forceinline__ C3 ld_c3(const Geo &gc, const double *__restrict__ ec, int Il,
+                                    int J, int mp)
+{
+    const int S = (gc.i0 + Il + J) & 1;  // colour of the even K in this coarse row
+    const long long row = ((long long)Il * gc.nj + J) * gc.kh;
+    const double *e0 = ec + (long long)S * gc.cs + row;
+    const double *e1 = ec + (long long)(S ^ 1) * gc.cs + row;
+    C3 r;
+    r.x = e0[mp];
+    r.y = e1[mp];
+    r.z = e0[mp + 1];
+    return r;
+}
+
+__device__ __forceinline__ double add0(double x) { return __dadd_rn(0., x); }
+
+// fine point with even k on coarse column x (ok = 0)
+__device__ __forceinline__ double pc_even(int oi, int oj, double a0, double a1, double b0,
+                                          double b1)
+{
+    if (!oi && !oj)
+        return a0;  // 1137-1138
+    if (oi && !oj)
+        return __dmul_rn(__dadd_rn(add0(a0), b0), 0.5);  // 1105-1111
+    if (!oi)
+        return __dmul_rn(__dadd_rn(add0(a0), a1), 0.5);  // 1112-1118
+    // 1080-1089: j fastest, then i
+    double t = __dadd_rn(add0(a0), a1);
+    t = __dadd_rn(t, b0);
+    t = __dadd_rn(t, b1);
+    return __dmul_rn(t, 0.25);
+}
+
+// fine point with odd k between coarse columns x (low) and y (high) (ok = 1)
+__device__ __forceinline__ double pc_odd(int oi, int oj, double a0x, double a0y, double a1x,
+                                         double a1y, double b0x, double b0y, double b1x,
+                                         double b1y)
+{
+    if (!oi && !oj)
+        return __dmul_rn(__dadd_rn(add0(a0x), a0y), 0.5);  // 1119-1125
+    if (oi && !oj) {  // 1070-1079: i fastest, then k
+        double t = __dadd_rn(add0(a0x), b0x);
+        t = __dadd_rn(t, a0y);
+        t = __dadd_rn(t, b0y);
+        return __dmul_rn(t, 0.25);
+    }
+    if (!oi) {  // 1059-1068: j fastest, then k
+        double t = __dadd_rn(add0(a0x), a1x);
+        t = __dadd_rn(t, a0y);
+        t = __dadd_rn(t, a1y);
+        return __dmul_rn(t, 0.25);
+    }
+    // 1023-1049: i-major, then j, then k
+    double t = __dadd_rn(add0(a0x), a0y);
+    t = __dadd_rn(t, a1x);
+    t = __dadd_rn(t, a1y);
+    t = __dadd_rn(t, b0x);
+    t = __dadd_rn(t, b0y);
+    t = __dadd_rn(t, b1x);
+    t = __dadd_rn(t, b1y);
+    return __dmul_rn(t, 0.125);
+}
+
 __global__ void __launch_bounds__(256)
 k_prolong_correct(Geo gc, const double *__restrict__ ec, Geo gf,
-                  double *__restrict__ ef, int il_lo, int il_hi)
+                  double *__restrict__ ef, int il_lo, int il_hi, int chunk)
 {
-    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long per_colour = (long long)(il_hi - il_lo) * gf.pj;
-    if (t >= 2 * per_colour)
+    const int npair = gf.kh >> 1;
+    const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= (gf.pj >> 1))
         return;
-    const int c = t >= per_colour;
-    const long long e = t - c * per_colour;
-    const int m = (int)(e % gf.kh);
-    const long long row = e / gf.kh;
-    const int j = (int)(row % gf.nj);
-    const int il = il_lo + (int)(row / gf.nj);
-    const int ig = gf.i0 + il;
-    const int k = 2 * m + ((c ^ (ig + j)) & 1);
-    if (k >= gf.nk)
+    const int j = (int)(q / npair);
+    const int mp = (int)(q - (long long)j * npair);
+    const int ia = il_lo + blockIdx.y * chunk;
+    const int ib = min(ia + chunk, il_hi);
+    if (ia >= ib)
         return;
-    const int oi = ig & 1, oj = j & 1, ok = k & 1;
-    const int I = (ig >> 1) - gc.i0, J = j >> 1, K = k >> 1;
-#define EC(a, b, cc_) rd_split(gc, ec, I + (a), J + (b), K + (cc_))
-    double add;
-    const int nodd = oi + oj + ok;
-    if (nodd == 3) {  // 1023-1049: i-major, then j, then k
-        add = __dadd_rn(0., EC(0, 0, 0));
-        add = __dadd_rn(add, EC(0, 0, 1));
-        add = __dadd_rn(add, EC(0, 1, 0));
-        add = __dadd_rn(add, EC(0, 1, 1));
-        add = __dadd_rn(add, EC(1, 0, 0));
-        add = __dadd_rn(add, EC(1, 0, 1));
-        add = __dadd_rn(add, EC(1, 1, 0));
-        add = __dadd_rn(add, EC(1, 1, 1));
-        add = __dmul_rn(add, 0.125);
-    } else if (nodd == 2) {
-        if (!oi) {  // 1059-1068: j fastest, then k
-            add = __dadd_rn(0., EC(0, 0, 0));
-            add = __dadd_rn(add, EC(0, 1, 0));
-            add = __dadd_rn(add, EC(0, 0, 1));
-            add = __dadd_rn(add, EC(0, 1, 1));
-        } else if (!oj) {  // 1070-1079: i fastest, then k
-            add = __dadd_rn(0., EC(0, 0, 0));
-            add = __dadd_rn(add, EC(1, 0, 0));
-            add = __dadd_rn(add, EC(0, 0, 1));
-            add = __dadd_rn(add, EC(1, 0, 1));
-        } else {  // 1080-1089: j fastest, then i
-            add = __dadd_rn(0., EC(0, 0, 0));
-            add = __dadd_rn(add, EC(0, 1, 0));
-            add = __dadd_rn(add, EC(1, 0, 0));
-            add = __dadd_rn(add, EC(1, 1, 0));
-        }
-        add = __dmul_rn(add, 0.25);
-    } else if (nodd == 1) {  // 1101-1134: low end, high end
-        add = __dadd_rn(0., EC(0, 0, 0));
-        add = __dadd_rn(add, EC(oi, oj, ok));
-        add = __dmul_rn(add, 0.5);
-    } else {  // 1137-1138
-        add = EC(0, 0, 0);
+    const int oj = j & 1, J0 = j >> 1;
+    const int k0 = 4 * mp;
+    if (k0 >= gf.nk)
+        return;  // pad columns only
+    const bool v1 = k0 + 1 < gf.nk, v2 = k0 + 2 < gf.nk, v3 = k0 + 3 < gf.nk;
+    const long long off = 2 * q;
+
+    C3 A0, A1, B0, B1;
+    {
+        const int I = ((gf.i0 + ia) >> 1) - gc.i0;
+        A0 = ld_c3(gc, ec, I, J0, mp);
+        A1 = oj ? ld_c3(gc, ec, I, J0 + 1, mp) : A0;
     }
-#undef EC
-    const long long idx = (long long)c * gf.cs + ((long long)il * gf.nj + j) * gf.kh + m;
-    ef[idx] = __dadd_rn(ef[idx], add);
+    B0 = A0;
+    B1 = A1;
+    for (int il = ia; il < ib; il++) {
+        const int ig = gf.i0 + il;
+        const int oi = ig & 1;
+        if (oi) {
+            const int I1 = (ig >> 1) + 1 - gc.i0;
+            B0 = ld_c3(gc, ec, I1, J0, mp);
+            B1 = oj ? ld_c3(gc, ec, I1, J0 + 1, mp) : B0;
+        }
+        const int s = (ig + j) & 1;  // colour holding the even k of this row
+        double *pe = ef + (long long)s * gf.cs + (long long)il * gf.pj + off;
+        double *po = ef + (long long)(s ^ 1) * gf.cs + (long long)il * gf.pj + off;
+        // even k: 4mp (coarse column x), 4mp+2 (column y)
+        const double e0 = pc_even(oi, oj, A0.x, A1.x, B0.x, B1.x);
+        const double e1 = pc_even(oi, oj, A0.y, A1.y, B0.y, B1.y);
+        // odd k: 4mp+1 (between x and y), 4mp+3 (between y and z)
+        const double o0 = pc_odd(oi, oj, A0.x, A0.y, A1.x, A1.y, B0.x, B0.y, B1.x, B1.y);
+        const double o1 = pc_odd(oi, oj, A0.y, A0.z, A1.y, A1.z, B0.y, B0.z, B1.y, B1.z);
+        if (v2) {
+            const double2 f = ld2(pe);
+            st2(pe, __dadd_rn(f.x, e0), __dadd_rn(f.y, e1));
+        } else {
+            pe[0] = __dadd_rn(pe[0], e0);
+        }
+        if (v3) {
+            const double2 f = ld2(po);
+            st2(po, __dadd_rn(f.x, o0), __dadd_rn(f.y, o1));
+        } else if (v1) {
+            po[0] = __dadd_rn(po[0], o0);
+        }
+        if (oi) {
+            A0 = B0;
+            A1 = B1;
+        }
+    }
 }
 
 void launch_prolong_correct(const Geo &gc, const double *ec, const Geo &gf,
@@ -530,9 +845,9 @@ void launch_prolong_correct(const Geo &gc, const double *ec, const Geo &gf,
 {
     if (il_hi <= il_lo)
         return;
-    const long long total = 2LL * (il_hi - il_lo) * gf.pj;
-    k_prolong_correct<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(gc, ec, gf, ef,
-                                                                      il_lo, il_hi);
+    static const int occ = resident_blocks(k_prolong_correct, 256, 0);
+    const MarchCfg c = march_cfg(gf, il_hi - il_lo, 256, occ);
+    k_prolong_correct<<<c.grid, c.block, 0, st>>>(gc, ec, gf, ef, il_lo, il_hi, c.chunk);
     COUNT_LAUNCH();
 }
 

@@ -32,6 +32,11 @@ void launch_residual(const Geo &g, const double *v, const double *d, double *r,
 void launch_restrict(const Geo &gf, const double *rf, const Geo &gc, double *dc,
                      int Il_lo, int Il_hi, cudaStream_t st);
 
+// the two above in one pass, the fine residual never stored (17 B/DOF)
+void launch_residual_restrict(const Geo &gf, const double *vf, const double *df,
+                              double invHsq, const Geo &gc, double *dc, int Il_lo,
+                              int Il_hi, cudaStream_t st);
+
 // trilinear prolongation + correction (mg_3d.h:1000-1145) for local fine
 // planes [il_lo, il_hi)
 void launch_prolong_correct(const Geo &gc, const double *ec, const Geo &gf,

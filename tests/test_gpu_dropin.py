@@ -1,0 +1,130 @@
+"""GPU: the drop-in C headers (multigrid_parallel_b200/compat) driven by C
+programs -- the reference's UNMODIFIED test_mg_3d.c (prebuilt where the
+reference is mounted; the binary travels to the GPU box) and the repo-owned
+poisson_dirichlet.c -- against the reference's own output (tests/golden)."""
+import hashlib
+import json
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+from oracle_lib import OrcMG, seeded
+
+pytestmark = pytest.mark.gpu
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+BUILD = os.path.join(ROOT, "multigrid_parallel_b200", "compat", "_build")
+GOLD = os.path.join(HERE, "golden")
+
+
+def _run(exe, args, cwd, threads, extra_env=None):
+    env = dict(os.environ, OMP_NUM_THREADS=str(threads))
+    env.update(extra_env or {})
+    p = subprocess.run([exe] + [str(a) for a in args], cwd=cwd, env=env, capture_output=True,
+                       text=True, timeout=600)
+    assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-2000:]
+    return p.stdout
+
+
+def _residual_lines(text):
+    out = []
+    for m in re.finditer(r"^\s*(\d+)\s+Residual Norm:\s*(\S+)\s+ResidRatio:\s*(\S+)", text, re.M):
+        out.append((int(m.group(1)), m.group(2), m.group(3)))
+    return out
+
+
+@pytest.mark.parametrize("threads", [1, 4])
+@pytest.mark.parametrize("lazy", ["1", "0"])
+def test_reference_driver_unmodified(tmp_path, threads, lazy):
+    exe = os.path.join(BUILD, "test_mg_3d_gpu")
+    if not os.path.exists(exe):
+        pytest.skip("test_mg_3d_gpu not prebuilt (needs /root/reference at build time)")
+    out = _run(exe, [3, 5, 2], tmp_path, threads, {"MGB_LAZY_SYNC": lazy})
+    gold = open(os.path.join(GOLD, "test_mg_3d_3_5_2.stdout")).read()
+    got, want = _residual_lines(out), _residual_lines(gold)
+    assert len(got) == len(want) == 14
+    for (ci, gn, gr), (cj, wn, wr) in zip(got, want):
+        assert ci == cj
+        # %20g shows 6 significant digits: identical text unless a digit
+        # boundary is straddled by the 1e-14 norm difference
+        assert float(gn) == pytest.approx(float(wn), rel=2e-6)
+        if ci > 1:
+            assert float(gr) == pytest.approx(float(wr), rel=2e-6)
+    # the error norm is computed by the driver on the host from the downloaded
+    # solution, which is bit-identical -> identical text
+    assert re.search(r"^Error norm:.*$", out, re.M).group(0) == \
+        re.search(r"^Error norm:.*$", gold, re.M).group(0)
+    # per-level timing table in the reference's format, 5 levels x 7 stages
+    assert out.count("LEVEL ") == 5 and out.count("Smoother1") == 5
+    assert re.search(r"^\s+Smoother1\s+14\s+\d+\.\d{6}$", out, re.M)
+    # the VTK file of the error field is byte-identical to the reference's
+    want_sha = open(os.path.join(GOLD, "test_mg_3d_3_5_2.vtk.sha256")).read().strip()
+    got_sha = hashlib.sha256(open(tmp_path / "diff2.vtk", "rb").read()).hexdigest()
+    assert got_sha == want_sha
+
+
+def test_reference_driver_usage_error(tmp_path):
+    exe = os.path.join(BUILD, "test_mg_3d_gpu")
+    if not os.path.exists(exe):
+        pytest.skip("test_mg_3d_gpu not prebuilt")
+    p = subprocess.run([exe, "3", "5"], cwd=tmp_path, capture_output=True, text=True)
+    assert p.returncode == 1 and p.stdout.startswith("Usage:")  # mg_3d.h:109-113
+
+
+@pytest.mark.parametrize("threads,lazy,profile", [(1, "1", "1"), (3, "1", "0"), (2, "0", "1")])
+def test_example_driver(tmp_path, orc, threads, lazy, profile):
+    exe = os.path.join(BUILD, "poisson_dirichlet")
+    assert os.path.exists(exe), "run __graft_entry__.build() first"
+    out = _run(exe, [3, 5, 2], tmp_path, threads,
+               {"MGB_LAZY_SYNC": lazy, "MGB_PROFILE": profile})
+    gold = json.load(open(os.path.join(GOLD, "histories.json")))["3_5_2"]
+    kv = {}
+    for line in out.splitlines():
+        parts = line.split()
+        if parts:
+            kv.setdefault(parts[0], []).append(parts[1:])
+    assert int(kv["cycles"][0][0]) == gold["cycles"]
+    norms = [float(p[2]) for p in kv["cycle"]]
+    assert np.allclose(norms, gold["history"], rtol=1e-12, atol=0)
+    assert float(kv["N"][0][4]) == gold["init_norm"]  # serial host sum: identical
+    err = kv["errnorm"][0]
+    assert float(err[4]) == gold["probe_1_2_3"]
+    assert float(err[0]) == pytest.approx(gold["errnorm_np"], rel=1e-9)
+    assert float(err[2]) == pytest.approx(gold["sumsq_np"], rel=1e-13)
+    # host write between solves reached the GPU: residual jumped, second solve
+    # needed cycles and restored the analytic value
+    assert float(kv["perturbed_residual"][0][0]) > 1e3
+    c2 = kv["cycles_after_perturbation"][0]
+    assert int(c2[0]) >= 5 and int(c2[2]) == int(c2[0])
+    assert float(kv["restored"][0][0]) < 1e-7
+    # raw-pointer smoother on caller arrays == oracle
+    M = 17
+    hm = 1.0 / (M - 1)
+    uu, dd = np.zeros((M,) * 3), np.zeros((M,) * 3)
+    orc.set_dirichlet(uu, hm)
+    init = orc.residual(uu, dd, hm)
+    orc.smooth(uu, dd, hm, 1, True)
+    orc.smooth(uu, dd, hm, 1, False)
+    after = orc.residual(uu, dd, hm)
+    rb = kv["rbgs17"][0]
+    assert float(rb[1]) == pytest.approx(init, rel=1e-13)
+    assert float(rb[3]) == pytest.approx(after, rel=1e-13)
+
+
+def test_example_driver_vtk(tmp_path):
+    exe = os.path.join(BUILD, "poisson_dirichlet")
+    out = _run(exe, [3, 4, 2], tmp_path, 2, {"MGB_WRITE_VTK": "out.vtk"})
+    text = open(tmp_path / "out.vtk").read().splitlines()
+    # postprocess.h:13-19,31,37-44
+    assert text[:6] == ["# vtk DataFile Version 2.0", "Potential data", "ASCII",
+                        "DATASET STRUCTURED_GRID", "DIMENSIONS 17 17 17", "POINTS 4913 float"]
+    assert text[6] == "0.00000000e+00 0.00000000e+00 0.00000000e+00"
+    assert text[7] == "0.00000000e+00 0.00000000e+00 6.25000000e-02"
+    n = 17 ** 3
+    assert text[6 + n] == "" and text[7 + n] == "POINT_DATA 4913"
+    assert text[8 + n] == "SCALARS data float 1" and text[9 + n] == "LOOKUP_TABLE default"
+    assert len(text) == 10 + 2 * n
