@@ -99,8 +99,10 @@ static void mgPull(MgMirror *m)
         return;
     mgProtect(m, PROT_READ | PROT_WRITE);
     MGB_OK(mgb_download(mgGpu, numLevels - 1, m->which, m->host));
-    m->state = MG_CLEAN;
-    mgProtect(m, PROT_READ); /* a later host write faults once and marks it dirty */
+    /* lazy mode: a later host write faults once and marks the pages dirty;
+     * explicit mode cannot see host writes, so assume one happens */
+    m->state = mgLazySync ? MG_CLEAN : MG_HOST_NEWER;
+    mgProtect(m, PROT_READ);
 }
 
 /* bring the device copy up to date (host -> device) */
