@@ -125,6 +125,31 @@ int mgb_timer_stop(mgb_solver *s, double *seconds);
 /* the solver's cudaStream_t (for interop, e.g. torch.cuda.ExternalStream) */
 void *mgb_stream(mgb_solver *s);
 
+/* ---- multi-GPU: one process per GPU, the i axis cut into slabs -----------
+ * The reference partitions every loop over i with `omp for schedule(static)`
+ * (mg_3d.h:658,681,729,753,807,962,1006); here rank p of P owns the planes
+ * [p*w, (p+1)*w), w = (ni-1)/P, plus halo planes, and after each colour
+ * half-sweep the freshly written boundary plane goes to the neighbour's halo
+ * over NCCL (NVLink).  Levels coarser than the first partitioned one are
+ * agglomerated on rank 0.  Results are bit-identical to the single-GPU path.
+ *   rank 0 : mgb_nccl_unique_id(buf[128]); ship buf to all ranks (any transport)
+ *   every  : mgb_create_dist(..., rank, nranks, buf, min_planes, min_points)
+ * In a partitioned solver mgb_upload/mgb_download/mgb_set_dirichlet address the
+ * rank's LOCAL planes [i0, i0+li) of mgb_local_range; norms are summed over
+ * the ranks; every compute entry point is collective over the ranks. */
+int mgb_nccl_unique_id(void *out128);
+int mgb_create_dist(mgb_solver **out, int ci, int cj, int ck, int levels,
+                    int gs_iters, int device, int rank, int nranks,
+                    const void *nccl_uid128, int min_planes_per_rank,
+                    long long min_points_per_rank /* < 0: default 2^20 */);
+int mgb_dist_info(const mgb_solver *s, int *rank, int *nranks, int *first_dist_level);
+int mgb_local_range(const mgb_solver *s, int level, int *i0, int *li, int *own_lo,
+                    int *own_hi);
+/* slab arithmetic, usable without a GPU */
+int mgb_plan_slab(int ni, int nranks, int rank, int *own_lo, int *own_hi);
+int mgb_plan_first_dist_level(int ci, int cj, int ck, int levels, int nranks,
+                              int min_planes, long long min_points);
+
 /* ---- stateless array entry points for the reference's raw-pointer API
  * (test_rb_gs_3d.c:70-81 and test_lu.c:33-42 call these on caller-owned host
  * arrays).  Each call stages host -> device, runs the CUDA kernels, stages

@@ -79,6 +79,13 @@ def load_library():
     L.mgb_timer_stop.argtypes = [vp, c_dp]
     L.mgb_stream.restype = C.c_void_p
     L.mgb_stream.argtypes = [vp]
+    L.mgb_nccl_unique_id.argtypes = [C.c_void_p]
+    L.mgb_create_dist.argtypes = [C.POINTER(vp), i, i, i, i, i, i, i, i, C.c_void_p, i,
+                                  C.c_longlong]
+    L.mgb_dist_info.argtypes = [vp, c_ip, c_ip, c_ip]
+    L.mgb_local_range.argtypes = [vp, i, c_ip, c_ip, c_ip, c_ip]
+    L.mgb_plan_slab.argtypes = [i, i, i, c_ip, c_ip]
+    L.mgb_plan_first_dist_level.argtypes = [i, i, i, i, i, i, C.c_longlong]
     L.mgb_host_smooth.argtypes = [c_dp, c_dp, i, i, i, d, i, i]
     L.mgb_host_residual.argtypes = [c_dp, c_dp, i, i, i, d, c_dp, c_dp]
     L.mgb_host_restrict.argtypes = [c_dp, i, i, i, c_dp, i, i, i]

@@ -11,6 +11,7 @@
 
 #include "../../include/mgb.h"
 #include "kernels.h"
+#include "nccl_dl.h"
 
 using namespace mgb;
 
@@ -96,6 +97,14 @@ struct Level {
     Geo g;
     double h, hSq, invHsq;
     DevArray a[3];  // MGB_U, MGB_D, MGB_R
+    // slab decomposition over i (multi-GPU): this rank owns the global planes
+    // [own_lo, own_hi) and stores `lower` halo planes below and `upper` above
+    bool dist = false;
+    int own_lo = 0, own_hi = 0;
+    int lower = 0, upper = 0;
+    // local plane range of the owned INTERIOR planes (what sweeps update)
+    int sweep_lo() const { return (own_lo > 1 ? own_lo : 1) - g.i0; }
+    int sweep_hi() const { return (own_hi < g.ni - 1 ? own_hi : g.ni - 1) - g.i0; }
 };
 
 struct StageMark {
@@ -128,6 +137,14 @@ struct mgb_solver {
     size_t ev_used = 0;
     std::vector<StageMark> marks;
     cudaEvent_t sw_a = nullptr, sw_b = nullptr;  // stopwatch
+    // multi-GPU: one process per GPU, slabs over i, NCCL over NVLink
+    int rank = 0, nranks = 1;
+    int LD = 0;  // levels >= LD are slab-partitioned, levels < LD live on rank 0
+    ncclComm_t comm = nullptr;
+    long long nccl_calls = 0;
+    bool is_dist() const { return nranks > 1; }
+    // does this rank compute on level q?
+    bool works_on(int q) const { return nranks == 1 || q >= LD || rank == 0; }
 };
 
 struct LaunchScope {
@@ -181,9 +198,54 @@ extern "C" int mgb_destroy(mgb_solver *s)
     if (s->lut) cudaFree(s->lut);
     if (s->cb) cudaFree(s->cb);
     if (s->cx) cudaFree(s->cx);
+    if (s->comm) nccl().CommDestroy(s->comm);
     if (s->st) cudaStreamDestroy(s->st);
     delete s;
     return 0;
+}
+
+// ----------------------------------------------------------------------------
+// slab planning (pure host arithmetic; also exported for the CPU-side tests)
+//
+// Level l has ni-1 = (ci-1)*2^l intervals along i.  Rank p of P owns the planes
+// [p*w, (p+1)*w) with w = (ni-1)/P, the last rank also the closing plane ni-1;
+// because w doubles with every refinement the cuts of all distributed levels
+// coincide (fine plane 2I belongs to the owner of coarse plane I).
+// ----------------------------------------------------------------------------
+extern "C" int mgb_plan_slab(int ni, int nranks, int rank, int *own_lo, int *own_hi)
+{
+    if (nranks < 1 || rank < 0 || rank >= nranks || ni < 3)
+        return fail("mgb_plan_slab: bad arguments");
+    if ((ni - 1) % nranks != 0)
+        return fail("%d intervals do not divide over %d ranks", ni - 1, nranks);
+    const int w = (ni - 1) / nranks;
+    *own_lo = rank * w;
+    *own_hi = rank == nranks - 1 ? ni : (rank + 1) * w;
+    return 0;
+}
+
+// first (coarsest) slab-partitioned level: every rank must own an even number
+// of planes (so the cut survives one more coarsening for the restriction
+// target), at least `min_planes` of them and at least `min_points` grid points
+// -- below that a level is latency-bound and cheaper on one GPU than split
+// with halo messages; level 0 always stays on rank 0
+extern "C" int mgb_plan_first_dist_level(int ci, int cj, int ck, int levels, int nranks,
+                                         int min_planes, long long min_points)
+{
+    if (nranks <= 1)
+        return 0;
+    if (min_planes < 2)
+        min_planes = 2;
+    for (int l = 1; l < levels; l++) {
+        const long long iv = (long long)(ci - 1) << l;
+        if (iv % nranks)
+            continue;
+        const long long w = iv / nranks;
+        const long long plane = (((long long)(cj - 1) << l) + 1) * (((long long)(ck - 1) << l) + 1);
+        if (w >= min_planes && w % 2 == 0 && w * plane >= min_points)
+            return l;
+    }
+    return levels;  // nothing can be partitioned
 }
 
 static bool pow2plus1(int n)
@@ -191,8 +253,9 @@ static bool pow2plus1(int n)
     return n >= 3 && ((n - 1) & (n - 2)) == 0;
 }
 
-extern "C" int mgb_create(mgb_solver **out, int ci, int cj, int ck, int levels,
-                          int gs_iters, int device)
+static int create_impl(mgb_solver **out, int ci, int cj, int ck, int levels, int gs_iters,
+                       int device, int rank, int nranks, const void *uid, int min_planes,
+                       long long min_points)
 {
     if (!out)
         return fail("out is null");
@@ -225,6 +288,21 @@ extern "C" int mgb_create(mgb_solver **out, int ci, int cj, int ck, int levels,
     s->device = device;
     s->L = levels;
     s->gs = gs_iters;
+    s->rank = rank;
+    s->nranks = nranks;
+    if (nranks > 1) {
+        if (levels < 2) {
+            delete s;
+            return fail("a partitioned solver needs at least 2 levels");
+        }
+        s->LD = mgb_plan_first_dist_level(ci, cj, ck, levels, nranks, min_planes, min_points);
+        if (s->LD >= levels) {
+            delete s;
+            return fail("no level of this hierarchy can be split over %d ranks with >= %d "
+                        "planes and >= %lld points each", nranks, min_planes, min_points);
+        }
+        s->opt_graph = 0;  // NCCL calls are issued eagerly between the kernels
+    }
     cudaError_t e = cudaSetDevice(device);
     if (e != cudaSuccess) {
         delete s;
@@ -252,7 +330,20 @@ extern "C" int mgb_create(mgb_solver **out, int ci, int cj, int ck, int levels,
         const int ni = (ci - 1) * (1 << l) + 1;  // mg_3d.h:41
         const int nj = (cj - 1) * (1 << l) + 1;
         const int nk = (ck - 1) * (1 << l) + 1;
-        lv.g = make_geo(ni, nj, nk, ni, 0);
+        lv.own_lo = 0;
+        lv.own_hi = ni;
+        if (nranks > 1 && l >= s->LD) {
+            lv.dist = true;
+            mgb_plan_slab(ni, nranks, rank, &lv.own_lo, &lv.own_hi);
+            // two planes below (the fused residual+restriction evaluates the
+            // residual on plane own_lo-1, which reads own_lo-2), one above
+            lv.lower = rank > 0 ? 2 : 0;
+            lv.upper = rank < nranks - 1 ? 1 : 0;
+            lv.g = make_geo(ni, nj, nk, lv.own_hi - lv.own_lo + lv.lower + lv.upper,
+                            lv.own_lo - lv.lower);
+        } else {
+            lv.g = make_geo(ni, nj, nk, ni, 0);
+        }
         // h_l = h_fine * 2^(L-1-l), formed by repeated doubling like
         // mg_3d.h:1303 (exact in binary either way)
         double h = hfine;
@@ -288,8 +379,85 @@ extern "C" int mgb_create(mgb_solver **out, int ci, int cj, int ck, int levels,
         mgb_destroy(s);
         return fail("coarsest grid has %lld unknowns > MGB_MAX_DENSE_N", nc);
     }
+    if (nranks > 1) {
+        if (!nccl().load()) {
+            fail("NCCL: %s", nccl().error);
+            mgb_destroy(s);
+            return 1;
+        }
+        ncclUniqueId id;
+        memcpy(&id, uid, sizeof id);
+        ncclResult_t r = nccl().CommInitRank(&s->comm, nranks, id, rank);
+        if (r != ncclSuccess) {
+            fail("ncclCommInitRank: %s", nccl().GetErrorString(r));
+            s->comm = nullptr;
+            mgb_destroy(s);
+            return 1;
+        }
+    }
 #undef CKD
     *out = s;
+    return 0;
+}
+
+extern "C" int mgb_create(mgb_solver **out, int ci, int cj, int ck, int levels,
+                          int gs_iters, int device)
+{
+    return create_impl(out, ci, cj, ck, levels, gs_iters, device, 0, 1, nullptr, 0, 0);
+}
+
+extern "C" int mgb_nccl_unique_id(void *out128)
+{
+    if (!out128)
+        return fail("out128 is null");
+    if (!nccl().load())
+        return fail("NCCL: %s", nccl().error);
+    ncclUniqueId id;
+    ncclResult_t r = nccl().GetUniqueId(&id);
+    if (r != ncclSuccess)
+        return fail("ncclGetUniqueId: %s", nccl().GetErrorString(r));
+    memcpy(out128, &id, sizeof id);
+    return 0;
+}
+
+extern "C" int mgb_create_dist(mgb_solver **out, int ci, int cj, int ck, int levels,
+                               int gs_iters, int device, int rank, int nranks,
+                               const void *nccl_uid128, int min_planes_per_rank,
+                               long long min_points_per_rank)
+{
+    if (nranks < 1 || rank < 0 || rank >= nranks)
+        return fail("rank %d / nranks %d out of range", rank, nranks);
+    if (nranks > 1 && !nccl_uid128)
+        return fail("nccl_uid128 is null");
+    if (nranks & (nranks - 1))
+        return fail("nranks must be a power of two (got %d)", nranks);
+    return create_impl(out, ci, cj, ck, levels, gs_iters, device, rank, nranks, nccl_uid128,
+                       min_planes_per_rank > 0 ? min_planes_per_rank : 16,
+                       min_points_per_rank >= 0 ? min_points_per_rank : (1LL << 20));
+}
+
+extern "C" int mgb_dist_info(const mgb_solver *s, int *rank, int *nranks, int *first_dist_level)
+{
+    if (!s)
+        return fail("null solver");
+    if (rank) *rank = s->rank;
+    if (nranks) *nranks = s->nranks;
+    if (first_dist_level) *first_dist_level = s->LD;
+    return 0;
+}
+
+extern "C" int mgb_local_range(const mgb_solver *s, int level, int *i0, int *li, int *own_lo,
+                               int *own_hi)
+{
+    if (!s)
+        return fail("null solver");
+    if (check_level(s, level, 0))
+        return 1;
+    const Level &lv = s->lv[level];
+    if (i0) *i0 = lv.g.i0;
+    if (li) *li = lv.g.li;
+    if (own_lo) *own_lo = lv.own_lo;
+    if (own_hi) *own_hi = lv.own_hi;
     return 0;
 }
 
@@ -327,9 +495,14 @@ extern "C" int mgb_set_option(mgb_solver *s, int key, int value)
     if (bind(s))
         return 1;
     switch (key) {
-    case MGB_OPT_GRAPH: s->opt_graph = value != 0; break;
+    case MGB_OPT_GRAPH: s->opt_graph = value != 0 && !s->is_dist(); break;
     case MGB_OPT_PROFILE: s->opt_profile = value != 0; break;
-    case MGB_OPT_FUSE: s->opt_fuse = value != 0; drop_graph(s); break;
+    case MGB_OPT_FUSE:
+        if (s->is_dist() && !value)
+            return fail("the partitioned solver only has the fused residual+restriction");
+        s->opt_fuse = value != 0;
+        drop_graph(s);
+        break;
     case MGB_OPT_GRAPH_LEVELS: break;
     default: return fail("unknown option %d", key);
     }
@@ -369,7 +542,7 @@ extern "C" int mgb_upload(mgb_solver *s, int level, int which, const double *hos
     if (!host)
         return fail("host pointer is null");
     Level &lv = s->lv[level];
-    const size_t n = (size_t)lv.g.ni * lv.g.nj * lv.g.nk;
+    const size_t n = (size_t)lv.g.li * lv.g.nj * lv.g.nk;  // local planes [i0, i0+li)
     if (need_stage(s, n))
         return 1;
     LaunchScope ls(s);
@@ -387,7 +560,7 @@ extern "C" int mgb_download(mgb_solver *s, int level, int which, double *host)
     if (!host)
         return fail("host pointer is null");
     Level &lv = s->lv[level];
-    const size_t n = (size_t)lv.g.ni * lv.g.nj * lv.g.nk;
+    const size_t n = (size_t)lv.g.li * lv.g.nj * lv.g.nk;
     if (need_stage(s, n))
         return 1;
     LaunchScope ls(s);
@@ -418,6 +591,81 @@ extern "C" int mgb_set_dirichlet(mgb_solver *s, int level, int which)
     return 0;
 }
 
+// ----------------------------------------------------------------------------
+// NCCL plumbing of the partitioned solver
+// ----------------------------------------------------------------------------
+static bool g_nccl_failed = false;
+#define NC(call)                                                       \
+    do {                                                               \
+        ncclResult_t r_ = (call);                                      \
+        if (r_ != ncclSuccess && !g_nccl_failed) {                     \
+            g_nccl_failed = true;                                      \
+            fail("%s -> %s", #call, nccl().GetErrorString(r_));        \
+        }                                                              \
+    } while (0)
+
+static int nccl_status()
+{
+    if (g_nccl_failed) {
+        g_nccl_failed = false;
+        return 1;
+    }
+    return 0;
+}
+
+// sum a device scalar over the ranks (rank order is NCCL's, fixed per topology)
+static void allreduce_scalar(mgb_solver *s, int slot)
+{
+    if (!s->is_dist())
+        return;
+    NC(nccl().AllReduce(s->d_scal + slot, s->d_scal + slot, 1, ncclDouble, ncclSum, s->comm,
+                        s->st));
+    s->nccl_calls++;
+}
+
+// one halo step on array `a` of a partitioned level, colours in `mask`
+// (bit c = colour c).  Planes are global indices, -1 = nothing:
+//   send_up   -> upper neighbour stores it as the same global plane
+//   recv_low  <- lower neighbour's send_up
+//   send_down -> lower neighbour;  recv_up <- upper neighbour's send_down
+static void halo_step(mgb_solver *s, Level &lv, double *a, int mask, int send_up, int recv_low,
+                      int send_down, int recv_up)
+{
+    const Geo &g = lv.g;
+    const bool has_low = s->rank > 0, has_up = s->rank < s->nranks - 1;
+    NC(nccl().GroupStart());
+    for (int c = 0; c < 2; c++) {
+        if (!(mask & (1 << c)))
+            continue;
+        double *base = a + (long long)c * g.cs;
+        const size_t n = (size_t)g.pj;
+        if (has_up && send_up >= 0)
+            NC(nccl().Send(base + (long long)(send_up - g.i0) * g.pj, n, ncclDouble, s->rank + 1,
+                           s->comm, s->st));
+        if (has_low && recv_low >= 0)
+            NC(nccl().Recv(base + (long long)(recv_low - g.i0) * g.pj, n, ncclDouble,
+                           s->rank - 1, s->comm, s->st));
+        if (has_low && send_down >= 0)
+            NC(nccl().Send(base + (long long)(send_down - g.i0) * g.pj, n, ncclDouble,
+                           s->rank - 1, s->comm, s->st));
+        if (has_up && recv_up >= 0)
+            NC(nccl().Recv(base + (long long)(recv_up - g.i0) * g.pj, n, ncclDouble, s->rank + 1,
+                           s->comm, s->st));
+    }
+    NC(nccl().GroupEnd());
+    s->nccl_calls++;
+}
+
+// after a half-sweep of `colour`: the freshly written boundary planes go to
+// the neighbours' halos (one colour-plane per neighbour)
+static void halo_after_sweep(mgb_solver *s, Level &lv, int colour)
+{
+    if (!lv.dist)
+        return;
+    halo_step(s, lv, lv.a[MGB_U].base, 1 << colour, lv.own_hi - 1, lv.own_lo - 1, lv.own_lo,
+              lv.own_hi);
+}
+
 static int fetch_scalar(mgb_solver *s, int slot, double *out)
 {
     CK(cudaMemcpyAsync(s->h_scal + slot, s->d_scal + slot, sizeof(double),
@@ -433,8 +681,19 @@ extern "C" int mgb_sumsq(mgb_solver *s, int level, int which, double *sumsq)
         return 1;
     Level &lv = s->lv[level];
     LaunchScope ls(s);
-    launch_sumsq(lv.a[which].base, 2 * lv.g.cs, s->partials, s->d_scal + 1, s->st);
+    // owned planes only (halos belong to the neighbours)
+    const long long first = (long long)(lv.own_lo - lv.g.i0) * lv.g.pj;
+    const long long n = (long long)(lv.own_hi - lv.own_lo) * lv.g.pj;
+    if (!s->works_on(level))
+        CK(cudaMemsetAsync(s->d_scal + 1, 0, sizeof(double), s->st));
+    else
+        launch_sumsq(lv.a[which].base + first, n, lv.a[which].base + lv.g.cs + first, n,
+                     s->partials, s->d_scal + 1, s->st);
     CKLAUNCH();
+    if (lv.dist)
+        allreduce_scalar(s, 1);
+    if (nccl_status())
+        return 1;
     return fetch_scalar(s, 1, sumsq);
 }
 
@@ -444,8 +703,13 @@ extern "C" int mgb_error_sumsq(mgb_solver *s, double *sumsq)
         return 1;
     Level &lv = s->lv[s->L - 1];
     LaunchScope ls(s);
-    launch_error_sumsq(lv.g, lv.a[MGB_U].base, lv.h, s->partials, s->d_scal + 2, s->st);
+    launch_error_sumsq(lv.g, lv.a[MGB_U].base, lv.h, lv.own_lo - lv.g.i0, lv.own_hi - lv.g.i0,
+                       s->partials, s->d_scal + 2, s->st);
     CKLAUNCH();
+    if (lv.dist)
+        allreduce_scalar(s, 2);
+    if (nccl_status())
+        return 1;
     return fetch_scalar(s, 2, sumsq);
 }
 
@@ -454,9 +718,12 @@ extern "C" int mgb_error_sumsq(mgb_solver *s, double *sumsq)
 // ----------------------------------------------------------------------------
 static void q_half_sweep(mgb_solver *s, int q, int colour)
 {
+    if (!s->works_on(q))
+        return;
     Level &lv = s->lv[q];
-    launch_half_sweep(lv.g, lv.a[MGB_U].base, lv.a[MGB_D].base, lv.hSq, colour, 1,
-                      lv.g.li - 1, s->st);
+    launch_half_sweep(lv.g, lv.a[MGB_U].base, lv.a[MGB_D].base, lv.hSq, colour, lv.sweep_lo(),
+                      lv.sweep_hi(), s->st);
+    halo_after_sweep(s, lv, colour);
 }
 
 static void q_smooth(mgb_solver *s, int q, int iters, int first_red)
@@ -470,34 +737,101 @@ static void q_smooth(mgb_solver *s, int q, int iters, int first_red)
 static void q_residual(mgb_solver *s, int q, bool store, int slot)
 {
     Level &lv = s->lv[q];
+    if (!s->works_on(q)) {
+        cudaMemsetAsync(s->d_scal + slot, 0, sizeof(double), s->st);
+        return;
+    }
     launch_residual(lv.g, lv.a[MGB_U].base, lv.a[MGB_D].base,
-                    store ? lv.a[MGB_R].base : nullptr, lv.invHsq, 1, lv.g.li - 1,
+                    store ? lv.a[MGB_R].base : nullptr, lv.invHsq, lv.sweep_lo(), lv.sweep_hi(),
                     s->partials, s->d_scal + slot, s->st);
+    if (lv.dist)
+        allreduce_scalar(s, slot);
 }
 
 static void q_restrict(mgb_solver *s, int q)
 {
+    if (!s->works_on(q))
+        return;
     Level &f = s->lv[q], &c = s->lv[q - 1];
     launch_restrict(f.g, f.a[MGB_R].base, c.g, c.a[MGB_D].base, 0, c.g.li, s->st);
 }
 
 static void q_residual_restrict(mgb_solver *s, int q)
 {
+    if (!s->works_on(q))
+        return;
     Level &f = s->lv[q], &c = s->lv[q - 1];
+    if (!f.dist) {
+        launch_residual_restrict(f.g, f.a[MGB_U].base, f.a[MGB_D].base, f.invHsq, c.g,
+                                 c.a[MGB_D].base, 0, c.g.li, s->st);
+        return;
+    }
+    // the residual on plane own_lo-1 (needed by my first coarse plane) reads
+    // the solution on own_lo-2: fetch that plane, both colours
+    halo_step(s, f, f.a[MGB_U].base, 3, f.own_hi - 2, f.own_lo - 2, -1, -1);
+    // my share of the coarse planes: those whose fine plane 2I I own
+    int Ilo, Ihi;
+    mgb_plan_slab(c.g.ni, s->nranks, s->rank, &Ilo, &Ihi);
     launch_residual_restrict(f.g, f.a[MGB_U].base, f.a[MGB_D].base, f.invHsq, c.g,
-                             c.a[MGB_D].base, 0, c.g.li, s->st);
+                             c.a[MGB_D].base, Ilo - c.g.i0, Ihi - c.g.i0, s->st);
+    if (c.dist) {
+        // the coarse rhs on plane own_lo-1 feeds the next restriction
+        halo_step(s, c, c.a[MGB_D].base, 3, c.own_hi - 1, c.own_lo - 1, -1, -1);
+    } else {
+        // agglomeration: gather the coarse rhs slabs on rank 0
+        NC(nccl().GroupStart());
+        for (int col = 0; col < 2; col++) {
+            double *base = c.a[MGB_D].base + (long long)col * c.g.cs;
+            if (s->rank > 0) {
+                NC(nccl().Send(base + (long long)Ilo * c.g.pj, (size_t)(Ihi - Ilo) * c.g.pj,
+                               ncclDouble, 0, s->comm, s->st));
+            } else {
+                for (int r = 1; r < s->nranks; r++) {
+                    int lo, hi;
+                    mgb_plan_slab(c.g.ni, s->nranks, r, &lo, &hi);
+                    NC(nccl().Recv(base + (long long)lo * c.g.pj, (size_t)(hi - lo) * c.g.pj,
+                                   ncclDouble, r, s->comm, s->st));
+                }
+            }
+        }
+        NC(nccl().GroupEnd());
+        s->nccl_calls++;
+    }
 }
 
 static void q_prolong(mgb_solver *s, int q)
 {
+    if (!s->works_on(q))
+        return;
     Level &f = s->lv[q], &c = s->lv[q - 1];
-    launch_prolong_correct(c.g, c.a[MGB_U].base, f.g, f.a[MGB_U].base, 0, f.g.li, s->st);
+    if (!f.dist) {
+        launch_prolong_correct(c.g, c.a[MGB_U].base, f.g, f.a[MGB_U].base, 0, f.g.li, s->st);
+        return;
+    }
+    // owned planes plus the nearest halo plane on each side: the neighbours
+    // compute the identical values, so no exchange is needed afterwards
+    const int lo = f.own_lo - (s->rank > 0 ? 1 : 0);
+    const int hi = f.own_hi + (s->rank < s->nranks - 1 ? 1 : 0);
+    launch_prolong_correct(c.g, c.a[MGB_U].base, f.g, f.a[MGB_U].base, lo - f.g.i0,
+                           hi - f.g.i0, s->st);
+}
+
+// after rank 0 has finished the agglomerated levels: everybody gets the
+// correction of level LD-1 (a small grid) for the prolongation
+static void q_broadcast_agglomerated(mgb_solver *s)
+{
+    Level &c = s->lv[s->LD - 1];
+    NC(nccl().Broadcast(c.a[MGB_U].base, c.a[MGB_U].base, (size_t)(2 * c.g.cs), ncclDouble, 0,
+                        s->comm, s->st));
+    s->nccl_calls++;
 }
 
 static void q_coarse_solve(mgb_solver *s)
 {
     // solveWithLU(LU, n, d[0], u[0]) (mg_3d.h:1270): the dense vectors are the
     // natural-layout views of level 0
+    if (!s->works_on(0))
+        return;
     Level &lv = s->lv[0];
     launch_unpack(lv.g, lv.a[MGB_D].base, s->cb, s->st);
     launch_lu_solve(s->lu, s->lut, s->nc, s->cb, s->cx, s->st);
@@ -516,7 +850,7 @@ extern "C" int mgb_half_sweep(mgb_solver *s, int level, int colour)
     OP_PROLOGUE(level, 0);
     q_half_sweep(s, level, colour ? 1 : 0);
     CKLAUNCH();
-    return 0;
+    return nccl_status();
 }
 
 extern "C" int mgb_smooth(mgb_solver *s, int level, int iters, int first_red)
@@ -524,14 +858,18 @@ extern "C" int mgb_smooth(mgb_solver *s, int level, int iters, int first_red)
     OP_PROLOGUE(level, 0);
     q_smooth(s, level, iters, first_red);
     CKLAUNCH();
-    return 0;
+    return nccl_status();
 }
 
 extern "C" int mgb_residual(mgb_solver *s, int level, int store_r, double *sumsq)
 {
     OP_PROLOGUE(level, 0);
+    if (store_r && s->is_dist())
+        return fail("the partitioned solver does not store the fine residual");
     q_residual(s, level, store_r != 0, 0);
     CKLAUNCH();
+    if (nccl_status())
+        return 1;
     if (sumsq)
         return fetch_scalar(s, 0, sumsq);
     return 0;
@@ -540,6 +878,8 @@ extern "C" int mgb_residual(mgb_solver *s, int level, int store_r, double *sumsq
 extern "C" int mgb_restrict(mgb_solver *s, int level)
 {
     OP_PROLOGUE(level, 1);
+    if (s->is_dist())
+        return fail("the partitioned solver only has the fused residual+restriction");
     q_restrict(s, level);
     CKLAUNCH();
     return 0;
@@ -550,15 +890,17 @@ extern "C" int mgb_residual_restrict(mgb_solver *s, int level)
     OP_PROLOGUE(level, 1);
     q_residual_restrict(s, level);
     CKLAUNCH();
-    return 0;
+    return nccl_status();
 }
 
 extern "C" int mgb_prolong_correct(mgb_solver *s, int level)
 {
     OP_PROLOGUE(level, 1);
+    if (s->is_dist() && level == s->LD)
+        q_broadcast_agglomerated(s);  // level LD-1 lives on rank 0
     q_prolong(s, level);
     CKLAUNCH();
-    return 0;
+    return nccl_status();
 }
 
 extern "C" int mgb_coarse_solve(mgb_solver *s)
@@ -628,6 +970,8 @@ struct StageTimer {
 static void enqueue_cycle(mgb_solver *s, int q, bool timed)
 {
     Level &lv = s->lv[q];
+    if (!s->works_on(q))
+        return;  // agglomerated levels run on rank 0 only
     if (q < s->L - 1)  // 1254-1260: coarse levels start from a zero guess
         cudaMemsetAsync(lv.a[MGB_U].base, 0, sizeof(double) * 2 * lv.g.cs, s->st);
     if (q == 0) {  // 1262-1277
@@ -656,6 +1000,8 @@ static void enqueue_cycle(mgb_solver *s, int q, bool timed)
     {
         StageTimer t(s, timed, q, MGB_ST_RECURSE);  // 1320
         enqueue_cycle(s, q - 1, timed);
+        if (s->is_dist() && q == s->LD)
+            q_broadcast_agglomerated(s);
     }
     {
         StageTimer t(s, timed, q, MGB_ST_PROLONG);  // 1331
@@ -722,6 +1068,8 @@ extern "C" int mgb_vcycle(mgb_solver *s, double *sumsq)
         enqueue_cycle(s, s->L - 1, true);
         s->launches += launches_issued() - before;
         CKLAUNCH();
+        if (nccl_status())
+            return 1;
         double v;
         if (fetch_scalar(s, 0, &v))
             return 1;
@@ -746,6 +1094,8 @@ extern "C" int mgb_vcycle(mgb_solver *s, double *sumsq)
         s->calls = saved;
         s->launches += launches_issued() - before;
         CKLAUNCH();
+        if (nccl_status())
+            return 1;
     }
     bump_calls_like_cycle(s);
     double v;

@@ -869,28 +869,34 @@ k_sumsq(const double *__restrict__ a, long long n, double *__restrict__ partials
         partials[blockIdx.x] = acc;
 }
 
-void launch_sumsq(const double *a, long long n, double *partials, double *out,
-                  cudaStream_t st)
+void launch_sumsq(const double *a0, long long n0, const double *a1, long long n1,
+                  double *partials, double *out, cudaStream_t st)
 {
-    long long nb = (n + 255) / 256;
+    long long nb = (n0 + 255) / 256;
     if (nb > 148 * 16)
         nb = 148 * 16;
     if (nb < 1)
         nb = 1;
-    k_sumsq<<<(unsigned)nb, 256, 0, st>>>(a, n, partials);
+    k_sumsq<<<(unsigned)nb, 256, 0, st>>>(a0, n0, partials);
     COUNT_LAUNCH();
-    k_finish_sum<<<1, 1024, 0, st>>>(partials, (int)nb, out);
+    int total = (int)nb;
+    if (a1 && n1 > 0) {
+        k_sumsq<<<(unsigned)nb, 256, 0, st>>>(a1, n1, partials + nb);
+        COUNT_LAUNCH();
+        total += (int)nb;
+    }
+    k_finish_sum<<<1, 1024, 0, st>>>(partials, total, out);
     COUNT_LAUNCH();
 }
 
 __global__ void __launch_bounds__(256)
-k_error_sumsq(Geo g, const double *__restrict__ u, double h,
+k_error_sumsq(Geo g, const double *__restrict__ u, double h, int il_lo, int il_hi,
               double *__restrict__ partials)
 {
     double acc = 0.;
-    const long long total = (long long)g.li * g.pj;
+    const long long first = (long long)il_lo * g.pj, total = (long long)il_hi * g.pj;
     const long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total;
+    for (long long t = first + (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total;
          t += stride) {
         const int m = (int)(t % g.kh);
         const long long row = t / g.kh;
@@ -914,14 +920,16 @@ k_error_sumsq(Geo g, const double *__restrict__ u, double h,
         partials[blockIdx.x] = acc;
 }
 
-void launch_error_sumsq(const Geo &g, const double *u, double h, double *partials,
-                        double *out, cudaStream_t st)
+void launch_error_sumsq(const Geo &g, const double *u, double h, int il_lo, int il_hi,
+                        double *partials, double *out, cudaStream_t st)
 {
-    const long long total = (long long)g.li * g.pj;
+    const long long total = (long long)(il_hi - il_lo) * g.pj;
     long long nb = (total + 255) / 256;
     if (nb > 148 * 16)
         nb = 148 * 16;
-    k_error_sumsq<<<(unsigned)nb, 256, 0, st>>>(g, u, h, partials);
+    if (nb < 1)
+        nb = 1;
+    k_error_sumsq<<<(unsigned)nb, 256, 0, st>>>(g, u, h, il_lo, il_hi, partials);
     COUNT_LAUNCH();
     k_finish_sum<<<1, 1024, 0, st>>>(partials, (int)nb, out);
     COUNT_LAUNCH();

@@ -42,11 +42,12 @@ void launch_residual_restrict(const Geo &gf, const double *vf, const double *df,
 void launch_prolong_correct(const Geo &gc, const double *ec, const Geo &gf,
                             double *ef, int il_lo, int il_hi, cudaStream_t st);
 
-// sum of squares of every stored entry (pads are zero) -> *out (device)
-void launch_sumsq(const double *a, long long n, double *partials, double *out,
-                  cudaStream_t st);
-// sum over all points of (u - BCFunc(ih,jh,kh))^2 (test_mg_3d.c:78-97)
-void launch_error_sumsq(const Geo &g, const double *u, double h,
+// sum of squares of the entries of one or two ranges (pads are zero) -> *out
+void launch_sumsq(const double *a0, long long n0, const double *a1, long long n1,
+                  double *partials, double *out, cudaStream_t st);
+// sum over the points of local planes [il_lo, il_hi) of (u - BCFunc(ih,jh,kh))^2
+// (test_mg_3d.c:78-97)
+void launch_error_sumsq(const Geo &g, const double *u, double h, int il_lo, int il_hi,
                         double *partials, double *out, cudaStream_t st);
 
 // dense coarse operator + LU (mg_3d.h:147-273, gauss_elim.h:9-60)

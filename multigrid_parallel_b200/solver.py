@@ -29,14 +29,49 @@ class Solver:
     side on level 0, `levels` grids, `gs` smoothing iterations per leg.
     """
 
-    def __init__(self, coarse, levels, gs, device=0):
+    def __init__(self, coarse, levels, gs, device=0, rank=0, nranks=1, nccl_uid=None,
+                 min_planes=16, min_points=-1):
         self.L = load_library()
         if isinstance(coarse, int):
             coarse = (coarse,) * 3
         self.h_ = C.c_void_p()
-        check(self.L.mgb_create(C.byref(self.h_), *coarse, levels, gs, device))
+        self.rank, self.nranks = rank, nranks
+        if nranks == 1:
+            check(self.L.mgb_create(C.byref(self.h_), *coarse, levels, gs, device))
+        else:
+            # slab-partitioned over i, one process per GPU (mgb_create_dist)
+            assert nccl_uid is not None and len(nccl_uid) == 128
+            buf = C.create_string_buffer(bytes(nccl_uid), 128)
+            check(self.L.mgb_create_dist(C.byref(self.h_), *coarse, levels, gs, device, rank,
+                                         nranks, buf, min_planes, min_points))
         self.levels = levels
         self.gs = gs
+
+    @staticmethod
+    def nccl_unique_id():
+        """rank 0: the 128-byte NCCL id every rank passes to the constructor"""
+        L = load_library()
+        buf = C.create_string_buffer(128)
+        check(L.mgb_nccl_unique_id(buf))
+        return buf.raw
+
+    def local_range(self, level=None):
+        """(i0, li, own_lo, own_hi): local planes [i0, i0+li), owned [own_lo, own_hi)"""
+        level = self.levels - 1 if level is None else level
+        a, b, c, d = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+        check(self.L.mgb_local_range(self.h_, level, a, b, c, d))
+        return a.value, b.value, c.value, d.value
+
+    def local_shape(self, level=None):
+        level = self.levels - 1 if level is None else level
+        ni, nj, nk = self.dims(level)
+        return (self.local_range(level)[1], nj, nk)
+
+    @property
+    def first_dist_level(self):
+        a, b, c = C.c_int(), C.c_int(), C.c_int()
+        check(self.L.mgb_dist_info(self.h_, a, b, c))
+        return c.value
 
     # -- lifecycle ---------------------------------------------------------
     def close(self):
@@ -76,7 +111,7 @@ class Solver:
     # -- arrays ------------------------------------------------------------
     def upload(self, level, which, host):
         host = np.ascontiguousarray(host, dtype=np.float64)
-        assert host.shape == self.dims(level), (host.shape, self.dims(level))
+        assert host.shape == self.local_shape(level), (host.shape, self.local_shape(level))
         check(self.L.mgb_upload(self.h_, level, which, host.ctypes.data))
 
     def upload_ptr(self, level, which, ptr):
@@ -84,7 +119,7 @@ class Solver:
 
     def download(self, level, which, out=None):
         if out is None:
-            out = np.empty(self.dims(level), dtype=np.float64)
+            out = np.empty(self.local_shape(level), dtype=np.float64)
         check(self.L.mgb_download(self.h_, level, which, out.ctypes.data))
         return out
 
