@@ -5,10 +5,12 @@ from /root/reference by oracle/Makefile).  Run in the build container:
 
 histories.json : per-cycle residual norms (test_mg_3d.c flow, tol 1e-8), cycle
 counts, error norms and checksums of the final solution for the configurations
-of SURVEY.md Appendix A.  Small cases are run with 1 OpenMP thread (bitwise
-reproducible by the serial oracle); --big adds 257^3 and 513^3, --huge 1025^3,
-run with all threads (the solution is thread-count invariant, the norms agree
-to ~1e-13).
+of SURVEY.md Appendix A.  Everything is run with ONE OpenMP thread, so the
+norms are bitwise reproducible by the serial oracle (the solution is
+thread-count invariant anyway; the reference's per-thread sequential norm sums
+are not: 8 threads differ from 1 thread by 1e-11 at 513^3 and 6e-10 at 1025^3,
+cf. SURVEY.md Appendix A).  --big adds 257^3 and 513^3, --huge 1025^3 (30 GB,
+~17 min).
 operators.json : checksums of every operator's output on seeded inputs.
 """
 import argparse
@@ -64,7 +66,7 @@ def main():
     huge = [(3, 10, 2)] if a.huge else []
     for coarse, levels, gs in cases + big + huge:
         key = f"{coarse}_{levels}_{gs}"
-        threads = 1 if (coarse, levels, gs) in cases else ref.L.ref_max_threads()
+        threads = 1
         ref.set_threads(threads)
         hist, init, u, secs = ref.solve(coarse, levels, gs, tol=1e-8, max_cycles=60)
         N = u.shape[0]

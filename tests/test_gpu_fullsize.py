@@ -9,8 +9,10 @@ adds them sequentially per OpenMP thread, which is itself only reproducible to
 ~1e-11 between team sizes at 513^3; the kernels use a tree whose result is
 within 1e-14 of the exactly rounded sum (test_exact_norm_of_identical_residual).
 Measured deviation of the reference's own one-thread sum from the exact one:
-<1e-12 up to 65^3, 5e-12 at 129^3.  Hence: 1e-12 up to 65^3, 1e-11 at 129^3,
-5e-11 at 257^3/513^3."""
+<1e-12 up to 65^3, 5e-12 at 129^3, and at 1025^3 the reference's 1-thread and
+8-thread norms differ from each other by 6.5e-10 (first cycle: golden
+309102136.013 vs SURVEY Appendix A 309102136.214).  Hence: 1e-12 up to 65^3,
+1e-11 at 129^3, 5e-11 at 257^3/513^3, 2e-9 at 1025^3."""
 import hashlib
 import json
 import math
@@ -41,8 +43,11 @@ def _solve(mgb, g, **opts):
 
 @pytest.mark.parametrize("key,rtol", [("3_5_2", 1e-12), ("3_5_1", 1e-12), ("3_5_3", 1e-12),
                                       ("5_4_2", 1e-12), ("9_3_2", 1e-12), ("3_6_2", 1e-12),
-                                      ("3_7_2", 1e-11), ("3_8_2", 5e-11), ("3_9_2", 5e-11)])
+                                      ("3_7_2", 1e-11), ("3_8_2", 5e-11), ("3_9_2", 5e-11),
+                                      ("3_10_2", 2e-9)])
 def test_solve_matches_reference_golden(mgb, histories, key, rtol):
+    if key not in histories:
+        pytest.skip(f"golden {key} not generated (oracle/gen_golden.py --huge)")
     g = histories[key]
     s, init, hist = _solve(mgb, g)
     # GetL2NormOfVector is a sequential sum in the reference (6e-12 off the exact
