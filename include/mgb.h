@@ -39,7 +39,9 @@ enum {                                             /* TimingInfo stages, mg_3d.h
 enum {                                             /* mgb_set_option keys */
     MGB_OPT_GRAPH = 0,      /* 1: replay the V-cycle as one CUDA graph (default 1)        */
     MGB_OPT_PROFILE = 1,    /* 1: per-stage CUDA-event timing, eager launches (default 0)  */
-    MGB_OPT_FUSE = 2,       /* 1: fused residual+restriction, r not stored (default 1)     */
+    MGB_OPT_FUSE = 2,       /* 0: every stage its own kernel, r stored; 1 (default): fused
+                             * residual+restriction, r not stored; 2: also the last colour
+                             * of each smoother leg inside the residual kernel that follows */
     MGB_OPT_GRAPH_LEVELS = 3/* only levels < this are graphed when PROFILE=1               */
 };
 
@@ -63,6 +65,13 @@ int mgb_levels(const mgb_solver *s);
 int mgb_dims(const mgb_solver *s, int level, int *ni, int *nj, int *nk);
 double mgb_spacing(const mgb_solver *s, int level);
 int mgb_set_option(mgb_solver *s, int key, int value);
+/* process-wide kernel selection (affects launches captured afterwards; CUDA
+ * graphs already built keep what they captured) */
+enum {
+    MGB_G_TILE = 0,           /* 1 (default): TMA tile kernels for residual / residual+restrict */
+    MGB_G_TILE_MIN_PLANE = 1  /* use them on levels with nj*nk >= value (default 40000)         */
+};
+int mgb_set_global(int key, long long value);
 int mgb_sync(mgb_solver *s);
 
 /* ---- level arrays: the reference hands out raw host pointers u[l], d[l],
@@ -96,6 +105,13 @@ int mgb_residual(mgb_solver *s, int level, int store_r, double *sumsq);
 int mgb_restrict(mgb_solver *s, int level);
 int mgb_residual_restrict(mgb_solver *s, int level);
 int mgb_prolong_correct(mgb_solver *s, int level);
+/* one colour of the smoother (mg_3d.h:681-702 / 753-773) and the stage that
+ * follows it in vcycle (mg_3d.h:1294+1310 resp. 1354) in ONE pass over the
+ * level: the new values never make a round trip through HBM before the
+ * residual reads them.  Same arithmetic as mgb_half_sweep followed by
+ * mgb_residual_restrict / mgb_residual(store_r=0), bit for bit. */
+int mgb_sweep_residual_restrict(mgb_solver *s, int level, int colour);
+int mgb_sweep_residual(mgb_solver *s, int level, int colour, double *sumsq);
 int mgb_coarse_solve(mgb_solver *s);
 /* the factorised coarse operator, row-major n x n (n = ci*cj*ck) */
 int mgb_coarse_lu_download(mgb_solver *s, double *host_lu);

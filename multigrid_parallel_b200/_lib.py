@@ -55,6 +55,7 @@ def load_library():
     L.mgb_spacing.argtypes = [vp, i]
     L.mgb_set_option.argtypes = [vp, i, i]
     L.mgb_sync.argtypes = [vp]
+    L.mgb_set_global.argtypes = [i, C.c_longlong]
     L.mgb_upload.argtypes = [vp, i, i, C.c_void_p]
     L.mgb_download.argtypes = [vp, i, i, C.c_void_p]
     L.mgb_zero.argtypes = [vp, i, i]
@@ -67,6 +68,8 @@ def load_library():
     L.mgb_restrict.argtypes = [vp, i]
     L.mgb_residual_restrict.argtypes = [vp, i]
     L.mgb_prolong_correct.argtypes = [vp, i]
+    L.mgb_sweep_residual_restrict.argtypes = [vp, i, i]
+    L.mgb_sweep_residual.argtypes = [vp, i, i, c_dp]
     L.mgb_coarse_solve.argtypes = [vp]
     L.mgb_coarse_lu_download.argtypes = [vp, C.c_void_p]
     L.mgb_vcycle.argtypes = [vp, c_dp]

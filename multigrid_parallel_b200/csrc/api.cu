@@ -498,13 +498,23 @@ extern "C" int mgb_set_option(mgb_solver *s, int key, int value)
     case MGB_OPT_GRAPH: s->opt_graph = value != 0 && !s->is_dist(); break;
     case MGB_OPT_PROFILE: s->opt_profile = value != 0; break;
     case MGB_OPT_FUSE:
-        if (s->is_dist() && !value)
+        if (s->is_dist() && value <= 0)
             return fail("the partitioned solver only has the fused residual+restriction");
-        s->opt_fuse = value != 0;
+        s->opt_fuse = value < 0 ? 0 : (value > 2 ? 2 : value);
         drop_graph(s);
         break;
     case MGB_OPT_GRAPH_LEVELS: break;
     default: return fail("unknown option %d", key);
+    }
+    return 0;
+}
+
+extern "C" int mgb_set_global(int key, long long value)
+{
+    switch (key) {
+    case MGB_G_TILE: tile_set(value != 0, -1); break;
+    case MGB_G_TILE_MIN_PLANE: tile_set(-1, value < 0 ? 0 : value); break;
+    default: return fail("unknown global option %d", key);
     }
     return 0;
 }
@@ -741,11 +751,27 @@ static void q_residual(mgb_solver *s, int q, bool store, int slot)
         cudaMemsetAsync(s->d_scal + slot, 0, sizeof(double), s->st);
         return;
     }
-    launch_residual(lv.g, lv.a[MGB_U].base, lv.a[MGB_D].base,
-                    store ? lv.a[MGB_R].base : nullptr, lv.invHsq, lv.sweep_lo(), lv.sweep_hi(),
-                    s->partials, s->d_scal + slot, s->st);
+    if (store ||
+        !launch_tile_residual(lv.g, lv.a[MGB_U].base, lv.a[MGB_D].base, lv.hSq, lv.invHsq, -1,
+                              lv.sweep_lo(), lv.sweep_hi(), s->partials, s->d_scal + slot, s->st))
+        launch_residual(lv.g, lv.a[MGB_U].base, lv.a[MGB_D].base,
+                        store ? lv.a[MGB_R].base : nullptr, lv.invHsq, lv.sweep_lo(),
+                        lv.sweep_hi(), s->partials, s->d_scal + slot, s->st);
     if (lv.dist)
         allreduce_scalar(s, slot);
+}
+
+// half-sweep of `colour` fused with the residual norm (tile.cu); falls back to
+// the two plain kernels where the tile kernel does not apply
+static void q_sweep_residual(mgb_solver *s, int q, int colour, int slot)
+{
+    Level &lv = s->lv[q];
+    if (s->works_on(q) && !lv.dist &&
+        launch_tile_residual(lv.g, lv.a[MGB_U].base, lv.a[MGB_D].base, lv.hSq, lv.invHsq, colour,
+                             lv.sweep_lo(), lv.sweep_hi(), s->partials, s->d_scal + slot, s->st))
+        return;
+    q_half_sweep(s, q, colour);
+    q_residual(s, q, false, slot);
 }
 
 static void q_restrict(mgb_solver *s, int q)
@@ -756,24 +782,38 @@ static void q_restrict(mgb_solver *s, int q)
     launch_restrict(f.g, f.a[MGB_R].base, c.g, c.a[MGB_D].base, 0, c.g.li, s->st);
 }
 
-static void q_residual_restrict(mgb_solver *s, int q)
+// residual + restriction; colour >= 0: the half-sweep of that colour is fused
+// in front (single-GPU levels; elsewhere it runs as its own kernel first)
+static void q_residual_restrict(mgb_solver *s, int q, int colour = -1)
 {
     if (!s->works_on(q))
         return;
     Level &f = s->lv[q], &c = s->lv[q - 1];
     if (!f.dist) {
-        launch_residual_restrict(f.g, f.a[MGB_U].base, f.a[MGB_D].base, f.invHsq, c.g,
-                                 c.a[MGB_D].base, 0, c.g.li, s->st);
+        if (colour >= 0 &&
+            launch_tile_residual_restrict(f.g, f.a[MGB_U].base, f.a[MGB_D].base, f.hSq, f.invHsq,
+                                          colour, c.g, c.a[MGB_D].base, 0, c.g.li, s->st))
+            return;
+        if (colour >= 0)
+            q_half_sweep(s, q, colour);
+        if (!launch_tile_residual_restrict(f.g, f.a[MGB_U].base, f.a[MGB_D].base, f.hSq, f.invHsq,
+                                           -1, c.g, c.a[MGB_D].base, 0, c.g.li, s->st))
+            launch_residual_restrict(f.g, f.a[MGB_U].base, f.a[MGB_D].base, f.invHsq, c.g,
+                                     c.a[MGB_D].base, 0, c.g.li, s->st);
         return;
     }
+    if (colour >= 0)
+        q_half_sweep(s, q, colour);
     // the residual on plane own_lo-1 (needed by my first coarse plane) reads
     // the solution on own_lo-2: fetch that plane, both colours
     halo_step(s, f, f.a[MGB_U].base, 3, f.own_hi - 2, f.own_lo - 2, -1, -1);
     // my share of the coarse planes: those whose fine plane 2I I own
     int Ilo, Ihi;
     mgb_plan_slab(c.g.ni, s->nranks, s->rank, &Ilo, &Ihi);
-    launch_residual_restrict(f.g, f.a[MGB_U].base, f.a[MGB_D].base, f.invHsq, c.g,
-                             c.a[MGB_D].base, Ilo - c.g.i0, Ihi - c.g.i0, s->st);
+    if (!launch_tile_residual_restrict(f.g, f.a[MGB_U].base, f.a[MGB_D].base, f.hSq, f.invHsq, -1,
+                                       c.g, c.a[MGB_D].base, Ilo - c.g.i0, Ihi - c.g.i0, s->st))
+        launch_residual_restrict(f.g, f.a[MGB_U].base, f.a[MGB_D].base, f.invHsq, c.g,
+                                 c.a[MGB_D].base, Ilo - c.g.i0, Ihi - c.g.i0, s->st);
     if (c.dist) {
         // the coarse rhs on plane own_lo-1 feeds the next restriction
         halo_step(s, c, c.a[MGB_D].base, 3, c.own_hi - 1, c.own_lo - 1, -1, -1);
@@ -893,6 +933,26 @@ extern "C" int mgb_residual_restrict(mgb_solver *s, int level)
     return nccl_status();
 }
 
+extern "C" int mgb_sweep_residual_restrict(mgb_solver *s, int level, int colour)
+{
+    OP_PROLOGUE(level, 1);
+    q_residual_restrict(s, level, colour ? 1 : 0);
+    CKLAUNCH();
+    return nccl_status();
+}
+
+extern "C" int mgb_sweep_residual(mgb_solver *s, int level, int colour, double *sumsq)
+{
+    OP_PROLOGUE(level, 0);
+    q_sweep_residual(s, level, colour ? 1 : 0, 0);
+    CKLAUNCH();
+    if (nccl_status())
+        return 1;
+    if (sumsq)
+        return fetch_scalar(s, 0, sumsq);
+    return 0;
+}
+
 extern "C" int mgb_prolong_correct(mgb_solver *s, int level)
 {
     OP_PROLOGUE(level, 1);
@@ -979,13 +1039,21 @@ static void enqueue_cycle(mgb_solver *s, int q, bool timed)
         q_coarse_solve(s);
         return;
     }
+    // opt_fuse >= 2: the last colour of each smoother leg rides inside the
+    // residual kernel that follows it (tile.cu); same arithmetic, same bits
+    const bool fuse_sweep = s->opt_fuse >= 2 && s->gs >= 1;
     {
         StageTimer t(s, timed, q, MGB_ST_SMOOTH1);  // 1282
-        q_smooth(s, q, s->gs, 1);
+        if (fuse_sweep) {
+            q_smooth(s, q, s->gs - 1, 1);
+            q_half_sweep(s, q, 1);
+        } else {
+            q_smooth(s, q, s->gs, 1);
+        }
     }
     if (s->opt_fuse) {
         StageTimer t(s, timed, q, MGB_ST_RESID1);  // 1294 + 1310 in one pass
-        q_residual_restrict(s, q);
+        q_residual_restrict(s, q, fuse_sweep ? 0 : -1);
         s->calls[(size_t)q * MGB_NUM_STAGES + MGB_ST_RESTRICT]++;
     } else {
         {
@@ -1007,15 +1075,23 @@ static void enqueue_cycle(mgb_solver *s, int q, bool timed)
         StageTimer t(s, timed, q, MGB_ST_PROLONG);  // 1331
         q_prolong(s, q);
     }
+    const bool fuse_post = fuse_sweep && q == s->L - 1;
     {
         StageTimer t(s, timed, q, MGB_ST_SMOOTH2);  // 1341
-        q_smooth(s, q, s->gs, 0);
+        if (fuse_post) {
+            q_smooth(s, q, s->gs - 1, 0);
+            q_half_sweep(s, q, 0);
+        } else {
+            q_smooth(s, q, s->gs, 0);
+        }
     }
     {
         // 1354: the reference evaluates the norm on every level but only the
         // finest one is ever used (test_mg_3d.c:45); coarser ones are elided
         StageTimer t(s, timed && q == s->L - 1, q, MGB_ST_RESID2);
-        if (q == s->L - 1)
+        if (fuse_post)
+            q_sweep_residual(s, q, 1, 0);
+        else if (q == s->L - 1)
             q_residual(s, q, false, 0);
     }
 }

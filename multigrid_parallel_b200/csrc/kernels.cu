@@ -153,6 +153,12 @@ __global__ void __launch_bounds__(256) k_unpack(Geo g, const double *__restrict_
         dst[ko] = split[(long long)(s ^ 1) * g.cs + t];
 }
 
+void launch_finish_sum(const double *partials, int n, double *out, cudaStream_t st)
+{
+    k_finish_sum<<<1, 1024, 0, st>>>(partials, n, out);
+    COUNT_LAUNCH();
+}
+
 void launch_pack(const Geo &g, const double *nat, double *split, cudaStream_t st)
 {
     const long long total = (long long)g.li * g.pj;

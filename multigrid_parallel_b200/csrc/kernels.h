@@ -50,6 +50,23 @@ void launch_sumsq(const double *a0, long long n0, const double *a1, long long n1
 void launch_error_sumsq(const Geo &g, const double *u, double h, int il_lo, int il_hi,
                         double *partials, double *out, cudaStream_t st);
 
+// second stage of every reduction: *out = sum of partials[0..n) in a fixed order
+void launch_finish_sum(const double *partials, int n, double *out, cudaStream_t st);
+
+// ---- tile kernels (tile.cu): plane-marching blocks fed by TMA bulk copies ----
+// Both return false (nothing launched) when the level does not suit them; the
+// caller then uses the plain kernels above.  colour < 0: no fused sweep;
+// colour = 0/1: the half-sweep of that colour over the same planes is fused in
+// (planes must then be ALL interior planes of the level, single-GPU levels only).
+bool tile_enabled();
+void tile_set(int on /* <0: keep */, long long min_plane /* <0: keep */);
+bool launch_tile_residual(const Geo &g, double *v, const double *d, double hSq, double invHsq,
+                          int colour, int il_lo, int il_hi, double *partials, double *out_sumsq,
+                          cudaStream_t st);
+bool launch_tile_residual_restrict(const Geo &gf, double *vf, const double *df, double hSq,
+                                   double invHsq, int colour, const Geo &gc, double *dc,
+                                   int Il_lo, int Il_hi, cudaStream_t st);
+
 // dense coarse operator + LU (mg_3d.h:147-273, gauss_elim.h:9-60)
 void launch_coarse_matrix(double *A, int ni, int nj, int nk, double h,
                           cudaStream_t st);

@@ -161,6 +161,14 @@ class Solver:
     def residual_restrict(self, level):
         check(self.L.mgb_residual_restrict(self.h_, level))
 
+    def sweep_residual_restrict(self, level, colour):
+        check(self.L.mgb_sweep_residual_restrict(self.h_, level, colour))
+
+    def sweep_residual(self, level, colour):
+        v = C.c_double()
+        check(self.L.mgb_sweep_residual(self.h_, level, colour, v))
+        return math.sqrt(v.value)
+
     def prolong_correct(self, level):
         check(self.L.mgb_prolong_correct(self.h_, level))
 
@@ -206,6 +214,14 @@ class Solver:
     @property
     def launch_count(self):
         return self.L.mgb_launch_count(self.h_)
+
+
+G_TILE, G_TILE_MIN_PLANE = 0, 1
+
+
+def set_global(key, value):
+    """process-wide kernel selection (mgb_set_global)"""
+    check(load_library().mgb_set_global(key, int(value)))
 
 
 # ---- stateless array entry points (the reference's raw-pointer API) -------

@@ -9,10 +9,14 @@ adds them sequentially per OpenMP thread, which is itself only reproducible to
 ~1e-11 between team sizes at 513^3; the kernels use a tree whose result is
 within 1e-14 of the exactly rounded sum (test_exact_norm_of_identical_residual).
 Measured deviation of the reference's own one-thread sum from the exact one:
-<1e-12 up to 65^3, 5e-12 at 129^3, and at 1025^3 the reference's 1-thread and
-8-thread norms differ from each other by 6.5e-10 (first cycle: golden
-309102136.013 vs SURVEY Appendix A 309102136.214).  Hence: 1e-12 up to 65^3,
-1e-11 at 129^3, 5e-11 at 257^3/513^3, 2e-9 at 1025^3."""
+<1e-12 up to 65^3, 5e-12 at 129^3, 2e-11 at 257^3, 2.6e-10 at 513^3
+(oracle/gen_exact_history.py prints them), and at 1025^3 the reference's
+1-thread and 8-thread norms differ from each other by 6.5e-10 (first cycle:
+golden 309102136.013 vs SURVEY Appendix A 309102136.214).  Hence, against the
+reference's PRINTED norms: 1e-12 up to 65^3, 1e-11 at 129^3, 5e-11 at 257^3,
+5e-10 at 513^3, 2e-9 at 1025^3 -- and against "history_exact" (the reference's
+own residual field after every cycle, summed in long double by
+oracle/gen_exact_history.py) 1e-13 at every size that has it."""
 import hashlib
 import json
 import math
@@ -43,7 +47,7 @@ def _solve(mgb, g, **opts):
 
 @pytest.mark.parametrize("key,rtol", [("3_5_2", 1e-12), ("3_5_1", 1e-12), ("3_5_3", 1e-12),
                                       ("5_4_2", 1e-12), ("9_3_2", 1e-12), ("3_6_2", 1e-12),
-                                      ("3_7_2", 1e-11), ("3_8_2", 5e-11), ("3_9_2", 5e-11),
+                                      ("3_7_2", 1e-11), ("3_8_2", 5e-11), ("3_9_2", 5e-10),
                                       ("3_10_2", 2e-9)])
 def test_solve_matches_reference_golden(mgb, histories, key, rtol):
     if key not in histories:
@@ -56,6 +60,10 @@ def test_solve_matches_reference_golden(mgb, histories, key, rtol):
     assert len(hist) == g["cycles"], "V-cycle count to 1e-8*||d|| differs from the reference"
     dev = np.max(np.abs(hist - np.array(g["history"])) / np.array(g["history"]))
     assert dev <= rtol, dev
+    if "history_exact" in g:  # the reference's residual fields, summed exactly
+        ex = np.array(g["history_exact"])
+        dev_exact = np.max(np.abs(hist - ex) / ex)
+        assert dev_exact <= 1e-13, dev_exact
     u = s.download(s.levels - 1, mgb.MGB_U)
     assert hashlib.sha256(u.tobytes()).hexdigest() == g["sha256"], "solution not bit-identical"
     assert float(u[1, 2, 3]) == g["probe_1_2_3"]

@@ -22,6 +22,20 @@ def _mk(mgb, coarse, levels, gs=2):
     return mgb.Solver(coarse, levels, gs)
 
 
+@pytest.fixture(params=["tile", "plain"], autouse=True)
+def kernel_family(request, mgb):
+    """every test runs twice: with the TMA tile kernels (tile.cu) forced onto
+    every level they can handle, and with the plain kernels only"""
+    if request.param == "tile":
+        mgb.set_global(mgb.G_TILE, 1)
+        mgb.set_global(mgb.G_TILE_MIN_PLANE, 0)
+    else:
+        mgb.set_global(mgb.G_TILE, 0)
+    yield request.param
+    mgb.set_global(mgb.G_TILE, 1)
+    mgb.set_global(mgb.G_TILE_MIN_PLANE, 40000)
+
+
 @pytest.mark.parametrize("coarse,levels", HIERARCHIES)
 def test_pack_roundtrip(mgb, coarse, levels):
     with _mk(mgb, coarse, levels) as s:
@@ -81,7 +95,7 @@ def test_residual(mgb, orc, coarse, levels):
             # norm-only form (res == NULL) leaves r alone
             s.upload(lvl, mgb.MGB_R, r0)
             got2 = s.residual(lvl, store_r=False)
-            assert got2 == got
+            assert got2 == pytest.approx(got, rel=NORM_RTOL)
             assert np.array_equal(s.download(lvl, mgb.MGB_R), r0)
 
 
@@ -113,6 +127,67 @@ def test_residual_restrict_fused_bitwise(mgb, orc, coarse, levels):
             orc.restrict(r, dc)
             s.residual_restrict(lvl)
             assert np.array_equal(s.download(lvl - 1, mgb.MGB_D), dc), f"level {lvl}"
+
+
+# hierarchies whose fine levels span several tiles of the tile kernels (tile.cu)
+BIG = [((3, 3, 3), 7), ((3, 5, 9), 5), ((5, 3, 3), 6), ((3, 3, 17), 5)]
+
+
+@pytest.mark.parametrize("coarse,levels", HIERARCHIES + BIG)
+@pytest.mark.parametrize("colour", [0, 1])
+def test_sweep_residual_fused_bitwise(mgb, orc, coarse, levels, colour):
+    """half-sweep + residual norm in one kernel == the two reference stages"""
+    with _mk(mgb, coarse, levels) as s:
+        for lvl in range(levels):
+            shape, h = s.dims(lvl), s.spacing(lvl)
+            v, d = seeded(shape, 51), seeded(shape, 52)
+            s.upload(lvl, mgb.MGB_U, v)
+            s.upload(lvl, mgb.MGB_D, d)
+            orc.half_sweep(v, d, h, colour)
+            want = orc.residual(v, d, h, None)
+            got = s.sweep_residual(lvl, colour)
+            assert np.array_equal(s.download(lvl, mgb.MGB_U), v), f"level {lvl}"
+            assert got == pytest.approx(want, rel=NORM_RTOL), f"level {lvl}"
+            # and the plain norm on the same state
+            assert s.residual(lvl, store_r=False) == pytest.approx(want, rel=NORM_RTOL)
+
+
+@pytest.mark.parametrize("coarse,levels", HIERARCHIES + BIG)
+@pytest.mark.parametrize("colour", [0, 1])
+def test_sweep_residual_restrict_fused_bitwise(mgb, orc, coarse, levels, colour):
+    """half-sweep + residual + restriction in one kernel == the three stages"""
+    with _mk(mgb, coarse, levels) as s:
+        for lvl in range(1, levels):
+            shape, h = s.dims(lvl), s.spacing(lvl)
+            v, d = seeded(shape, 53), seeded(shape, 54)
+            s.upload(lvl, mgb.MGB_U, v)
+            s.upload(lvl, mgb.MGB_D, d)
+            s.upload(lvl - 1, mgb.MGB_D, seeded(s.dims(lvl - 1), 55))  # must be overwritten
+            orc.half_sweep(v, d, h, colour)
+            r = np.zeros(shape)
+            orc.residual(v, d, h, r)
+            dc = np.zeros(s.dims(lvl - 1))
+            orc.restrict(r, dc)
+            s.sweep_residual_restrict(lvl, colour)
+            assert np.array_equal(s.download(lvl, mgb.MGB_U), v), f"level {lvl}"
+            assert np.array_equal(s.download(lvl - 1, mgb.MGB_D), dc), f"level {lvl}"
+
+
+@pytest.mark.parametrize("coarse,levels", BIG)
+def test_residual_restrict_big_bitwise(mgb, orc, coarse, levels):
+    with _mk(mgb, coarse, levels) as s:
+        lvl = levels - 1
+        shape, h = s.dims(lvl), s.spacing(lvl)
+        v, d = seeded(shape, 56), seeded(shape, 57)
+        s.upload(lvl, mgb.MGB_U, v)
+        s.upload(lvl, mgb.MGB_D, d)
+        r = np.zeros(shape)
+        want = orc.residual(v, d, h, r)
+        dc = np.zeros(s.dims(lvl - 1))
+        orc.restrict(r, dc)
+        s.residual_restrict(lvl)
+        assert np.array_equal(s.download(lvl - 1, mgb.MGB_D), dc)
+        assert s.residual(lvl, store_r=False) == pytest.approx(want, rel=NORM_RTOL)
 
 
 @pytest.mark.parametrize("coarse,levels", HIERARCHIES)
@@ -209,7 +284,7 @@ def test_stateless_transfer_operators(mgb, orc):
 
 
 @pytest.mark.parametrize("coarse,levels,gs", [((3, 3, 3), 5, 2), ((5, 5, 5), 3, 1), ((3, 5, 9), 4, 3)])
-@pytest.mark.parametrize("mode", ["graph", "eager", "profile", "unfused"])
+@pytest.mark.parametrize("mode", ["graph", "eager", "profile", "unfused", "fuse1", "fuse2"])
 def test_vcycle_bitwise_all_levels(mgb, orc, coarse, levels, gs, mode):
     """one and several V-cycles: every level's u and d match the oracle bit
     for bit, the returned norm to 1e-13"""
@@ -222,6 +297,10 @@ def test_vcycle_bitwise_all_levels(mgb, orc, coarse, levels, gs, mode):
             s.set_option(OPT_PROFILE, 1)
         elif mode == "unfused":
             s.set_option(OPT_FUSE, 0)
+        elif mode == "fuse1":
+            s.set_option(OPT_FUSE, 1)
+        elif mode == "fuse2":
+            s.set_option(OPT_FUSE, 2)
         top = levels - 1
         u0, d0 = seeded(s.dims(top), 41), seeded(s.dims(top), 42)
         mg.u(top)[...] = u0
