@@ -33,6 +33,20 @@ TOL = 1e-8                            # test_mg_3d.c:19
 METRIC = "vcycle_dof_per_s"
 UNIT = "DOF*cycles/s"
 HALF_SWEEP_BYTES_PER_DOF = 12.0       # read 1/2 v, read 1/2 d, write 1/2 v
+# SURVEY 8(d) algorithmic bytes per DOF of the other finest-level stages
+STAGE_BYTES_PER_DOF = {"CalcResidual1": ("k_tile<-1,restrict> (residual+restrict)", 17.0),
+                       "Prolongate&Correct": ("k_prolong_correct8", 17.0),
+                       "CalcResidual2": ("k_tile<-1,norm> (residual norm)", 16.0)}
+
+
+def ncu_traffic(kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` from the
+    committed `ncu --set full` summary (profiles/traffic.json), or None"""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        return t[kernel]["dram_bytes_per_launch"]
+    except Exception:
+        return None
 
 
 def measured_peak_gbs():
@@ -222,6 +236,14 @@ def run_ours(args):
     t_half = (stage[0] + stage[5]) / n_half
     achieved = HALF_SWEEP_BYTES_PER_DOF * dof / t_half / 1e9
     share = (stage[0] + stage[5]) / (sum(stage[st] for st in range(7)))
+    others = {}
+    for st in range(7):
+        name = m.STAGE_NAMES[st]
+        if name in STAGE_BYTES_PER_DOF and stage[st] > 0:
+            kern, bpd = STAGE_BYTES_PER_DOF[name]
+            gbs = bpd * dof / stage[st] / 1e9
+            others[kern] = {"achieved": gbs, "frac": gbs / peak, "bytes_per_dof": bpd,
+                            "launch_us": stage[st] * 1e6}
 
     # end to end through the C ABI with host buffers (pinned), whole solve
     import torch
@@ -273,10 +295,11 @@ def run_ours(args):
                 "step": "one full solve: upload grid+rhs from pinned host memory, V-cycles to "
                         "1e-8*||d||, download grid"},
         "roofline": {"bound": "hbm", "kernel": "k_half_sweep", "achieved": achieved, "peak": peak,
-                     "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                     "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic("k_half_sweep"),
                      "peak_source": peak_src, "bytes_per_dof": HALF_SWEEP_BYTES_PER_DOF,
                      "avg_launch_us": t_half * 1e6, "share_of_finest_level": share,
-                     "frac_of_8TBs_nominal": achieved / 8000.0},
+                     "frac_of_8TBs_nominal": achieved / 8000.0,
+                     "other_kernels": others},
         "stage_us_finest": {m.STAGE_NAMES[st]: stage[st] * 1e6 for st in range(7)},
         "cpu_baseline": cpu,
     }

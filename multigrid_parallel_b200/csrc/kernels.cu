@@ -846,11 +846,161 @@ k_prolong_correct(Geo gc, const double *__restrict__ ec, Geo gf,
     }
 }
 
+// ----------------------------------------------------------------------------
+// prolongation + correction, wide form: a thread owns EIGHT consecutive fine
+// points k = 8q..8q+7 of one fine row (two 16-byte pairs of each colour) and
+// marches over fine planes in (even, odd) pairs.  The five coarse entries
+// K = 4q..4q+4 it interpolates from come as two 128-bit loads + one scalar per
+// coarse row; coarse plane I+1 is fetched at the top of a pair and becomes
+// plane I of the next one.  The fine values of the NEXT pair are loaded before
+// the current pair is stored, into a second register set (the pair loop is
+// unrolled by two, so no in-flight value is ever copied): every thread keeps
+// 256 B of reads in flight, which is what the read-modify-write stream needs.
+// ----------------------------------------------------------------------------
+struct C5 {
+    double v[5];  // coarse entries K = 4q .. 4q+4
+};
+
+__device__ __forceinline__ C5 ld_c5(const Geo &gc, const double *__restrict__ ec, int Il, int J,
+                                    int q)
+{
+    const int S = (gc.i0 + Il + J) & 1;  // colour of the even K in this coarse row
+    const long long row = ((long long)Il * gc.nj + J) * gc.kh + 2 * q;
+    const double *e0 = ec + (long long)S * gc.cs + row;
+    const double *e1 = ec + (long long)(S ^ 1) * gc.cs + row;
+    const double2 a = ld2(e0), b = ld2(e1);
+    C5 r;
+    r.v[0] = a.x; r.v[1] = b.x; r.v[2] = a.y; r.v[3] = b.y;
+    r.v[4] = e0[2];
+    return r;
+}
+
+struct F8 {
+    double2 e0, e1, o0, o1;  // even-k colour entries 4q..4q+3, odd-k colour entries
+};
+
+__global__ void __launch_bounds__(256, 2)
+k_prolong_correct8(Geo gc, const double *__restrict__ ec, Geo gf, double *ef, int il_lo,
+                   int il_hi, int chunk)
+{
+    const int noct = gf.kh >> 2;
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (long long)gf.nj * noct)
+        return;
+    const int j = (int)(t / noct);
+    const int q = (int)(t - (long long)j * noct);
+    const int ia = il_lo + blockIdx.y * chunk;
+    const int ib = min(ia + chunk, il_hi);
+    const int k0 = 8 * q;
+    if (ia >= ib || k0 >= gf.nk)
+        return;  // pad columns only
+    const int oj = j & 1, J0 = j >> 1;
+    const int nvalid = min(8, gf.nk - k0);  // fine points k0 .. k0+nvalid-1 exist
+    const long long off = (long long)j * gf.kh + 4 * q;
+
+    auto load_f = [&](int il, F8 &f) {
+        const int s = (gf.i0 + il + j) & 1;  // colour holding the even k of this row
+        const double *pe = ef + (long long)s * gf.cs + (long long)il * gf.pj + off;
+        const double *po = ef + (long long)(s ^ 1) * gf.cs + (long long)il * gf.pj + off;
+        f.e0 = ld2(pe); f.e1 = ld2(pe + 2);
+        f.o0 = ld2(po); f.o1 = ld2(po + 2);
+    };
+    // add the interpolated correction of one fine plane and store it
+    auto plane = [&](int il, int oi, const C5 &A0, const C5 &A1, const C5 &B0, const C5 &B1,
+                     const F8 &f) {
+        double ev[4], od[4];
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+            ev[e] = pc_even(oi, oj, A0.v[e], A1.v[e], B0.v[e], B1.v[e]);
+            od[e] = pc_odd(oi, oj, A0.v[e], A0.v[e + 1], A1.v[e], A1.v[e + 1], B0.v[e],
+                           B0.v[e + 1], B1.v[e], B1.v[e + 1]);
+        }
+        const int s = (gf.i0 + il + j) & 1;
+        double *pe = ef + (long long)s * gf.cs + (long long)il * gf.pj + off;
+        double *po = ef + (long long)(s ^ 1) * gf.cs + (long long)il * gf.pj + off;
+        const double r0 = __dadd_rn(f.e0.x, ev[0]), r1 = __dadd_rn(f.e0.y, ev[1]);
+        const double r2 = __dadd_rn(f.e1.x, ev[2]), r3 = __dadd_rn(f.e1.y, ev[3]);
+        const double w0 = __dadd_rn(f.o0.x, od[0]), w1 = __dadd_rn(f.o0.y, od[1]);
+        const double w2 = __dadd_rn(f.o1.x, od[2]), w3 = __dadd_rn(f.o1.y, od[3]);
+        if (nvalid == 8) {
+            st2(pe, r0, r1); st2(pe + 2, r2, r3);
+            st2(po, w0, w1); st2(po + 2, w2, w3);
+        } else {  // last octet of the row: even k = k0+2e, odd k = k0+2e+1
+            if (nvalid > 0) pe[0] = r0;
+            if (nvalid > 2) pe[1] = r1;
+            if (nvalid > 4) pe[2] = r2;
+            if (nvalid > 6) pe[3] = r3;
+            if (nvalid > 1) po[0] = w0;
+            if (nvalid > 3) po[1] = w1;
+            if (nvalid > 5) po[2] = w2;
+        }
+    };
+
+    int il = ia;
+    int I = ((gf.i0 + il) >> 1) - gc.i0;  // coarse plane at or below fine plane il
+    C5 A0 = ld_c5(gc, ec, I, J0, q);
+    C5 A1 = oj ? ld_c5(gc, ec, I, J0 + 1, q) : A0;
+    if ((gf.i0 + il) & 1) {  // chunk starts on an odd plane: do it on its own
+        const C5 B0 = ld_c5(gc, ec, I + 1, J0, q);
+        const C5 B1 = oj ? ld_c5(gc, ec, I + 1, J0 + 1, q) : B0;
+        F8 f;
+        load_f(il, f);
+        plane(il, 1, A0, A1, B0, B1, f);
+        A0 = B0; A1 = B1;
+        I++; il++;
+    }
+    if (il >= ib)
+        return;
+    // from here il is even: pairs (il, il+1)
+    F8 Pe, Po, Qe, Qo;
+    Po = F8{};
+    Qe = F8{}; Qo = F8{};
+    load_f(il, Pe);
+    if (il + 1 < ib)
+        load_f(il + 1, Po);
+    auto pair = [&](F8 &ce, F8 &co, F8 &ne, F8 &no) {
+        const bool has_odd = il + 1 < ib;
+        C5 B0 = A0, B1 = A1;
+        if (has_odd) {  // coarse plane I+1: used by the odd plane, then becomes A
+            B0 = ld_c5(gc, ec, I + 1, J0, q);
+            B1 = oj ? ld_c5(gc, ec, I + 1, J0 + 1, q) : B0;
+        }
+        if (il + 2 < ib)
+            load_f(il + 2, ne);
+        if (il + 3 < ib)
+            load_f(il + 3, no);
+        plane(il, 0, A0, A1, A0, A1, ce);
+        if (has_odd)
+            plane(il + 1, 1, A0, A1, B0, B1, co);
+        A0 = B0; A1 = B1;
+        I++; il += 2;
+    };
+    while (il < ib) {
+        pair(Pe, Po, Qe, Qo);
+        if (il < ib)
+            pair(Qe, Qo, Pe, Po);
+    }
+}
+
 void launch_prolong_correct(const Geo &gc, const double *ec, const Geo &gf,
                             double *ef, int il_lo, int il_hi, cudaStream_t st)
 {
     if (il_hi <= il_lo)
         return;
+    static const int wide = getenv("MGB_PROLONG_WIDE") ? atoi(getenv("MGB_PROLONG_WIDE")) : 1;
+    if (wide) {
+        static const int occ8 = resident_blocks(k_prolong_correct8, 256, 0);
+        const long long items = (long long)gf.nj * (gf.kh >> 2);
+        const unsigned bx = (unsigned)((items + 255) / 256);
+        const int nplanes = il_hi - il_lo;
+        int nch = pick_chunks(bx, nplanes, occ8);
+        int chunk = (nplanes + nch - 1) / nch;
+        chunk += chunk & 1;  // whole (even, odd) pairs per chunk
+        const unsigned by = (unsigned)((nplanes + chunk - 1) / chunk);
+        k_prolong_correct8<<<dim3(bx, by), 256, 0, st>>>(gc, ec, gf, ef, il_lo, il_hi, chunk);
+        COUNT_LAUNCH();
+        return;
+    }
     static const int occ = resident_blocks(k_prolong_correct, 256, 0);
     const MarchCfg c = march_cfg(gf, il_hi - il_lo, 256, occ);
     k_prolong_correct<<<c.grid, c.block, 0, st>>>(gc, ec, gf, ef, il_lo, il_hi, c.chunk);
