@@ -190,7 +190,7 @@ def run_ours(args):
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.gpus != world and world > 1:
         raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
-    if world > 1:
+    if world > 1 or args.problem != "weak":
         from multigrid_parallel_b200 import dist_bench
         return dist_bench.run(args, rank, world, local_rank)
 
@@ -315,6 +315,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--problem", default="weak", choices=["weak", "strong1025"],
+                    help="weak (default): 513^3 per GPU; strong1025: the 1025^3 cube of BASELINE "
+                         "config 4 on --gpus GPUs (extra mode, no e2e leg)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

@@ -65,6 +65,7 @@ struct DevArray {
     size_t bytes = 0;
 };
 
+static Geo make_geo(int ni, int nj, int nk, int li, int i0);
 static Geo make_geo(int ni, int nj, int nk, int li, int i0)
 {
     Geo g;
@@ -112,6 +113,16 @@ struct StageMark {
     cudaEvent_t a, b;
 };
 
+// the neighbouring rank on one side of the slab: its level arrays and flag
+// block mapped into this process (CUDA IPC), and its local geometry
+struct PeerSide {
+    bool present = false;
+    std::vector<double *> arr[2];  // [MGB_U / MGB_D][level]: colour 0, local plane 0
+    std::vector<Geo> g;            // [level]
+    unsigned long long *flags = nullptr;
+    std::vector<void *> opened;    // cudaIpcOpenMemHandle results
+};
+
 struct mgb_solver {
     int device = 0;
     int L = 0, gs = 0;
@@ -129,6 +140,7 @@ struct mgb_solver {
     int opt_graph = 1, opt_profile = 0, opt_fuse = 1;
     cudaGraphExec_t gexec = nullptr;
     long long graph_launches = 0;
+    int eager_cycles = 0;  // partitioned solver: cycles run eagerly before the capture
     // bookkeeping
     long long launches = 0;
     std::vector<double> secs;  // L*7
@@ -142,6 +154,18 @@ struct mgb_solver {
     int LD = 0;  // levels >= LD are slab-partitioned, levels < LD live on rank 0
     ncclComm_t comm = nullptr;
     long long nccl_calls = 0;
+    // every NCCL call runs on its own stream, ordered against the kernel stream
+    // by events, so that a halo exchange can overlap the interior of a sweep
+    cudaStream_t st_comm = nullptr;
+    cudaEvent_t ev_m2c = nullptr, ev_c2m = nullptr;
+    int opt_overlap = 0;
+    // halo planes over NVLink peer memory instead of ncclSend/Recv:
+    // xflags[0]/[1] = sequence flags written by the lower / upper neighbour,
+    // [2]/[3] = my sequence numbers towards up / low, [4]/[5] = what I expect
+    // next from low / up, [6]/[7] = block counters of the push kernels
+    int opt_p2p = 1;
+    PeerSide low, up;
+    unsigned long long *xflags = nullptr;
     bool is_dist() const { return nranks > 1; }
     // does this rank compute on level q?
     bool works_on(int q) const { return nranks == 1 || q >= LD || rank == 0; }
@@ -198,7 +222,14 @@ extern "C" int mgb_destroy(mgb_solver *s)
     if (s->lut) cudaFree(s->lut);
     if (s->cb) cudaFree(s->cb);
     if (s->cx) cudaFree(s->cx);
+    for (PeerSide *ps : {&s->low, &s->up})
+        for (void *p : ps->opened)
+            cudaIpcCloseMemHandle(p);
+    if (s->xflags) cudaFree(s->xflags);
     if (s->comm) nccl().CommDestroy(s->comm);
+    if (s->st_comm) { cudaStreamSynchronize(s->st_comm); cudaStreamDestroy(s->st_comm); }
+    if (s->ev_m2c) cudaEventDestroy(s->ev_m2c);
+    if (s->ev_c2m) cudaEventDestroy(s->ev_c2m);
     if (s->st) cudaStreamDestroy(s->st);
     delete s;
     return 0;
@@ -246,6 +277,136 @@ extern "C" int mgb_plan_first_dist_level(int ci, int cj, int ck, int levels, int
             return l;
     }
     return levels;  // nothing can be partitioned
+}
+
+// ----------------------------------------------------------------------------
+// peer mapping of the neighbours' arrays (CUDA IPC) for the P2P halo exchange
+// ----------------------------------------------------------------------------
+struct IpcRec {
+    cudaIpcMemHandle_t h;
+    unsigned long long offset;  // of the pointer inside its cudaMalloc block
+    unsigned long long pad;
+};
+
+typedef int (*MemRangeFn)(unsigned long long *, size_t *, unsigned long long);
+
+static bool ipc_record(MemRangeFn range, void *ptr, IpcRec *rec)
+{
+    unsigned long long base = 0;
+    size_t size = 0;
+    if (range(&base, &size, (unsigned long long)ptr) != 0)
+        return false;
+    memset(rec, 0, sizeof *rec);
+    rec->offset = (unsigned long long)ptr - base;
+    return cudaIpcGetMemHandle(&rec->h, (void *)base) == cudaSuccess;
+}
+
+static Geo make_geo(int ni, int nj, int nk, int li, int i0);
+
+// local geometry of level `lv` on rank r (the same arithmetic create_impl uses)
+static Geo rank_geo(const Geo &mine, int nranks, int r)
+{
+    int lo = 0, hi = 0;
+    mgb_plan_slab(mine.ni, nranks, r, &lo, &hi);
+    const int lower = r > 0 ? 2 : 0, upper = r < nranks - 1 ? 1 : 0;
+    return make_geo(mine.ni, mine.nj, mine.nk, hi - lo + lower + upper, lo - lower);
+}
+
+// returns 0 when both neighbours are mapped; any failure leaves the solver on
+// the NCCL path (the caller makes the decision collective)
+static int setup_p2p_local(mgb_solver *s, std::vector<IpcRec> &all, int count)
+{
+    for (int side = 0; side < 2; side++) {
+        const int r = side == 0 ? s->rank - 1 : s->rank + 1;
+        PeerSide &ps = side == 0 ? s->low : s->up;
+        if (r < 0 || r >= s->nranks)
+            continue;
+        ps.arr[0].assign(s->L, nullptr);
+        ps.arr[1].assign(s->L, nullptr);
+        ps.g.assign(s->L, Geo{});
+        std::vector<std::pair<IpcRec, void *>> seen;
+        auto map = [&](const IpcRec &rec) -> void * {
+            for (auto &e : seen)
+                if (!memcmp(&e.first.h, &rec.h, sizeof rec.h))
+                    return (char *)e.second + rec.offset;
+            void *base = nullptr;
+            if (cudaIpcOpenMemHandle(&base, rec.h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+                cudaGetLastError();
+                return nullptr;
+            }
+            ps.opened.push_back(base);
+            seen.push_back({rec, base});
+            return (char *)base + rec.offset;
+        };
+        const IpcRec *recs = &all[(size_t)r * count];
+        ps.flags = (unsigned long long *)map(recs[0]);
+        if (!ps.flags)
+            return 1;
+        for (int l = s->LD; l < s->L; l++)
+            for (int w = 0; w < 2; w++) {
+                void *p = map(recs[1 + 2 * (l - s->LD) + w]);
+                if (!p)
+                    return 1;
+                ps.arr[w][l] = (double *)p + MGB_GUARD;
+                ps.g[l] = rank_geo(s->lv[l].g, s->nranks, r);
+            }
+        ps.present = true;
+    }
+    return 0;
+}
+
+static int setup_p2p(mgb_solver *s)
+{
+    int ok = 1;
+    MemRangeFn range = nullptr;
+    {
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuMemGetAddressRange", &fn, cudaEnableDefault, &q) ==
+                cudaSuccess && q == cudaDriverEntryPointSuccess)
+            range = (MemRangeFn)fn;
+        else
+            ok = 0;
+    }
+    const int count = 1 + 2 * (s->L - s->LD);
+    std::vector<IpcRec> mine(count), all((size_t)count * s->nranks);
+    if (cudaMalloc(&s->xflags, 4096) != cudaSuccess || cudaMemset(s->xflags, 0, 4096) != cudaSuccess)
+        ok = 0;
+    if (ok) {
+        ok = ipc_record(range, s->xflags, &mine[0]);
+        for (int l = s->LD; ok && l < s->L; l++)
+            for (int w = 0; ok && w < 2; w++)
+                ok = ipc_record(range, s->lv[l].a[w].alloc, &mine[1 + 2 * (l - s->LD) + w]);
+    }
+    // everybody learns everybody's handles (the exchange itself is collective
+    // even if this rank already failed)
+    char *dsend = nullptr, *drecv = nullptr;
+    const size_t bytes = sizeof(IpcRec) * count;
+    CK(cudaMalloc(&dsend, bytes));
+    CK(cudaMalloc(&drecv, bytes * s->nranks));
+    CK(cudaMemcpy(dsend, mine.data(), bytes, cudaMemcpyHostToDevice));
+    ncclResult_t r = nccl().AllGather(dsend, drecv, bytes, ncclChar, s->comm, s->st);
+    if (r != ncclSuccess)
+        return fail("ncclAllGather: %s", nccl().GetErrorString(r));
+    CK(cudaStreamSynchronize(s->st));
+    CK(cudaMemcpy(all.data(), drecv, bytes * s->nranks, cudaMemcpyDeviceToHost));
+    if (ok && setup_p2p_local(s, all, count))
+        ok = 0;
+    // collective decision: P2P only if every rank mapped its neighbours
+    int *dflag = (int *)dsend;
+    CK(cudaMemcpy(dflag, &ok, sizeof ok, cudaMemcpyHostToDevice));
+    r = nccl().AllReduce(dflag, dflag, 1, ncclInt, ncclMin, s->comm, s->st);
+    if (r != ncclSuccess)
+        return fail("ncclAllReduce: %s", nccl().GetErrorString(r));
+    CK(cudaStreamSynchronize(s->st));
+    CK(cudaMemcpy(&ok, dflag, sizeof ok, cudaMemcpyDeviceToHost));
+    cudaFree(dsend);
+    cudaFree(drecv);
+    s->opt_p2p = ok;
+    if (getenv("MGB_VERBOSE"))
+        fprintf(stderr, "mgb: rank %d halo exchange over %s\n", s->rank,
+                ok ? "NVLink peer memory (P2P stores + flags)" : "ncclSend/ncclRecv");
+    return 0;
 }
 
 static bool pow2plus1(int n)
@@ -385,6 +546,11 @@ static int create_impl(mgb_solver **out, int ci, int cj, int ck, int levels, int
             mgb_destroy(s);
             return 1;
         }
+        CKD(cudaStreamCreateWithFlags(&s->st_comm, cudaStreamNonBlocking));
+        CKD(cudaEventCreateWithFlags(&s->ev_m2c, cudaEventDisableTiming));
+        CKD(cudaEventCreateWithFlags(&s->ev_c2m, cudaEventDisableTiming));
+        if (getenv("MGB_OVERLAP"))
+            s->opt_overlap = atoi(getenv("MGB_OVERLAP")) != 0;
         ncclUniqueId id;
         memcpy(&id, uid, sizeof id);
         ncclResult_t r = nccl().CommInitRank(&s->comm, nranks, id, rank);
@@ -394,6 +560,18 @@ static int create_impl(mgb_solver **out, int ci, int cj, int ck, int levels, int
             mgb_destroy(s);
             return 1;
         }
+        if (getenv("MGB_P2P"))
+            s->opt_p2p = atoi(getenv("MGB_P2P")) != 0;
+        if (s->opt_p2p && setup_p2p(s)) {
+            mgb_destroy(s);
+            return 1;
+        }
+        // with the halo exchange as plain kernels (device-side sequence numbers)
+        // the whole partitioned cycle replays as one CUDA graph per rank; the
+        // three NCCL calls left in it are capturable
+        s->opt_graph = s->opt_p2p;
+        if (getenv("MGB_DIST_GRAPH"))
+            s->opt_graph = s->opt_p2p && atoi(getenv("MGB_DIST_GRAPH")) != 0;
     }
 #undef CKD
     *out = s;
@@ -495,7 +673,7 @@ extern "C" int mgb_set_option(mgb_solver *s, int key, int value)
     if (bind(s))
         return 1;
     switch (key) {
-    case MGB_OPT_GRAPH: s->opt_graph = value != 0 && !s->is_dist(); break;
+    case MGB_OPT_GRAPH: s->opt_graph = value != 0 && (!s->is_dist() || s->opt_p2p); break;
     case MGB_OPT_PROFILE: s->opt_profile = value != 0; break;
     case MGB_OPT_FUSE:
         if (s->is_dist() && value <= 0)
@@ -530,6 +708,8 @@ extern "C" int mgb_sync(mgb_solver *s)
 // ----------------------------------------------------------------------------
 // level arrays across the boundary
 // ----------------------------------------------------------------------------
+static void halo_fence(mgb_solver *s, Level &lv);  // P2P halo exchange, below
+
 static int need_stage(mgb_solver *s, size_t n)
 {
     if (s->stage_n >= n)
@@ -558,6 +738,7 @@ extern "C" int mgb_upload(mgb_solver *s, int level, int which, const double *hos
     LaunchScope ls(s);
     CK(cudaMemcpyAsync(s->stage, host, sizeof(double) * n, cudaMemcpyHostToDevice, s->st));
     launch_pack(lv.g, s->stage, lv.a[which].base, s->st);
+    halo_fence(s, lv);
     CKLAUNCH();
     CK(cudaStreamSynchronize(s->st));
     return 0;
@@ -587,6 +768,7 @@ extern "C" int mgb_zero(mgb_solver *s, int level, int which)
         return 1;
     Level &lv = s->lv[level];
     CK(cudaMemsetAsync(lv.a[which].base, 0, sizeof(double) * 2 * lv.g.cs, s->st));
+    halo_fence(s, lv);
     return 0;
 }
 
@@ -597,6 +779,7 @@ extern "C" int mgb_set_dirichlet(mgb_solver *s, int level, int which)
     Level &lv = s->lv[level];
     LaunchScope ls(s);
     launch_set_dirichlet(lv.g, lv.a[which].base, lv.h, s->st);
+    halo_fence(s, lv);
     CKLAUNCH();
     return 0;
 }
@@ -623,13 +806,36 @@ static int nccl_status()
     return 0;
 }
 
+// the communication stream picks up after everything enqueued on the kernel
+// stream so far ...
+// (with the P2P halo exchange the few remaining NCCL calls -- norm all-reduce,
+// agglomeration gather / broadcast -- simply run on the kernel stream)
+static cudaStream_t nccl_stream(mgb_solver *s) { return s->opt_p2p ? s->st : s->st_comm; }
+static void comm_begin(mgb_solver *s)
+{
+    if (s->opt_p2p)
+        return;
+    cudaEventRecord(s->ev_m2c, s->st);
+    cudaStreamWaitEvent(s->st_comm, s->ev_m2c, 0);
+}
+// ... and the kernel stream continues once the communication enqueued so far is done
+static void comm_end(mgb_solver *s)
+{
+    if (s->opt_p2p)
+        return;
+    cudaEventRecord(s->ev_c2m, s->st_comm);
+    cudaStreamWaitEvent(s->st, s->ev_c2m, 0);
+}
+
 // sum a device scalar over the ranks (rank order is NCCL's, fixed per topology)
 static void allreduce_scalar(mgb_solver *s, int slot)
 {
     if (!s->is_dist())
         return;
+    comm_begin(s);
     NC(nccl().AllReduce(s->d_scal + slot, s->d_scal + slot, 1, ncclDouble, ncclSum, s->comm,
-                        s->st));
+                        nccl_stream(s)));
+    comm_end(s);
     s->nccl_calls++;
 }
 
@@ -638,11 +844,58 @@ static void allreduce_scalar(mgb_solver *s, int slot)
 //   send_up   -> upper neighbour stores it as the same global plane
 //   recv_low  <- lower neighbour's send_up
 //   send_down -> lower neighbour;  recv_up <- upper neighbour's send_down
+// phases of a halo step: the P2P path can separate the push of my planes from
+// the wait for the neighbours' (other work goes in between); NCCL does both in
+// HALO_PUSH and nothing in HALO_WAIT
+enum { HALO_BOTH = 0, HALO_PUSH = 1, HALO_WAIT = 2 };
+
+// `bracket` (NCCL path): order the exchange after the kernel stream and make the
+// kernel stream wait for it (false: the caller places comm_begin / comm_end itself)
 static void halo_step(mgb_solver *s, Level &lv, double *a, int mask, int send_up, int recv_low,
-                      int send_down, int recv_up)
+                      int send_down, int recv_up, bool bracket = true, int phase = HALO_BOTH)
 {
     const Geo &g = lv.g;
     const bool has_low = s->rank > 0, has_up = s->rank < s->nranks - 1;
+    if (s->opt_p2p) {
+        const int q = (int)(&lv - &s->lv[0]);
+        const int w = a == lv.a[MGB_U].base ? MGB_U : MGB_D;
+        if (phase != HALO_WAIT) {
+            HaloRun run[2];  // 0: to the upper neighbour, 1: to the lower
+            for (int dir = 0; dir < 2; dir++) {
+                const PeerSide &ps = dir == 0 ? s->up : s->low;
+                const int plane = dir == 0 ? send_up : send_down;
+                if (!(dir == 0 ? has_up : has_low) || plane < 0)
+                    continue;
+                const Geo &gn = ps.g[q];
+                int k = 0;
+                for (int c = 0; c < 2; c++) {
+                    if (!(mask & (1 << c)))
+                        continue;
+                    run[dir].src[k] = a + (long long)c * g.cs + (long long)(plane - g.i0) * g.pj;
+                    run[dir].dst[k] =
+                        ps.arr[w][q] + (long long)c * gn.cs + (long long)(plane - gn.i0) * gn.pj;
+                    run[dir].n[k] = g.pj;
+                    k++;
+                }
+                // the neighbour's flag I write: its "from low" if I am below it
+                run[dir].peer_flag = ps.flags + (dir == 0 ? 0 : 1);
+                run[dir].seq = s->xflags + (dir == 0 ? 2 : 3);
+                run[dir].done = (unsigned int *)(s->xflags + (dir == 0 ? 6 : 7));
+            }
+            launch_halo_push(run[0], run[1], s->st);
+        }
+        if (phase != HALO_PUSH) {
+            const bool wl = has_low && recv_low >= 0, wu = has_up && recv_up >= 0;
+            launch_halo_wait(wl ? s->xflags + 0 : nullptr, s->xflags + 4,
+                             wu ? s->xflags + 1 : nullptr, s->xflags + 5, s->st);
+        }
+        s->nccl_calls++;
+        return;
+    }
+    if (phase == HALO_WAIT)
+        return;
+    if (bracket)
+        comm_begin(s);
     NC(nccl().GroupStart());
     for (int c = 0; c < 2; c++) {
         if (!(mask & (1 << c)))
@@ -651,29 +904,46 @@ static void halo_step(mgb_solver *s, Level &lv, double *a, int mask, int send_up
         const size_t n = (size_t)g.pj;
         if (has_up && send_up >= 0)
             NC(nccl().Send(base + (long long)(send_up - g.i0) * g.pj, n, ncclDouble, s->rank + 1,
-                           s->comm, s->st));
+                           s->comm, s->st_comm));
         if (has_low && recv_low >= 0)
             NC(nccl().Recv(base + (long long)(recv_low - g.i0) * g.pj, n, ncclDouble,
-                           s->rank - 1, s->comm, s->st));
+                           s->rank - 1, s->comm, s->st_comm));
         if (has_low && send_down >= 0)
             NC(nccl().Send(base + (long long)(send_down - g.i0) * g.pj, n, ncclDouble,
-                           s->rank - 1, s->comm, s->st));
+                           s->rank - 1, s->comm, s->st_comm));
         if (has_up && recv_up >= 0)
             NC(nccl().Recv(base + (long long)(recv_up - g.i0) * g.pj, n, ncclDouble, s->rank + 1,
-                           s->comm, s->st));
+                           s->comm, s->st_comm));
     }
     NC(nccl().GroupEnd());
+    if (bracket)
+        comm_end(s);
     s->nccl_calls++;
+}
+
+// P2P path only.  A push lands in the neighbour's halo planes whenever the
+// SENDER gets there; ncclRecv, by contrast, is ordered in the receiver's stream.
+// Wherever a rank writes its own halo planes with a local kernel (the zero
+// guess of a coarse level, the redundant halo update of the prolongation,
+// uploads), it therefore tells both neighbours when that is done, and waits
+// for the same from them, before anybody pushes into those planes again: a
+// data-less halo step.
+static void halo_fence(mgb_solver *s, Level &lv)
+{
+    if (!lv.dist || !s->opt_p2p)
+        return;
+    halo_step(s, lv, lv.a[MGB_U].base, 0, 0, 0, 0, 0);
 }
 
 // after a half-sweep of `colour`: the freshly written boundary planes go to
 // the neighbours' halos (one colour-plane per neighbour)
-static void halo_after_sweep(mgb_solver *s, Level &lv, int colour)
+static void halo_after_sweep(mgb_solver *s, Level &lv, int colour, bool bracket = true,
+                             int phase = HALO_BOTH)
 {
     if (!lv.dist)
         return;
     halo_step(s, lv, lv.a[MGB_U].base, 1 << colour, lv.own_hi - 1, lv.own_lo - 1, lv.own_lo,
-              lv.own_hi);
+              lv.own_hi, bracket, phase);
 }
 
 static int fetch_scalar(mgb_solver *s, int slot, double *out)
@@ -731,8 +1001,33 @@ static void q_half_sweep(mgb_solver *s, int q, int colour)
     if (!s->works_on(q))
         return;
     Level &lv = s->lv[q];
-    launch_half_sweep(lv.g, lv.a[MGB_U].base, lv.a[MGB_D].base, lv.hSq, colour, lv.sweep_lo(),
-                      lv.sweep_hi(), s->st);
+    const int lo = lv.sweep_lo(), hi = lv.sweep_hi();
+    // worth it only where the interior of the sweep outlasts the exchange by far:
+    // >= 4M points per slab (off by default: MGB_OVERLAP=1)
+    if (lv.dist && s->opt_overlap && hi - lo >= 4 &&
+        (long long)(hi - lo) * lv.g.nj * lv.g.nk >= (4LL << 20)) {
+        // the two planes the neighbours are waiting for first; their exchange then
+        // runs on the communication stream underneath the interior of the sweep
+        // (within a colour the order of the updates does not matter)
+        launch_half_sweep(lv.g, lv.a[MGB_U].base, lv.a[MGB_D].base, lv.hSq, colour, lo, lo + 1,
+                          s->st);
+        launch_half_sweep(lv.g, lv.a[MGB_U].base, lv.a[MGB_D].base, lv.hSq, colour, hi - 1, hi,
+                          s->st);
+        if (s->opt_p2p) {
+            halo_after_sweep(s, lv, colour, false, HALO_PUSH);
+            launch_half_sweep(lv.g, lv.a[MGB_U].base, lv.a[MGB_D].base, lv.hSq, colour, lo + 1,
+                              hi - 1, s->st);
+            halo_after_sweep(s, lv, colour, false, HALO_WAIT);
+            return;
+        }
+        comm_begin(s);
+        halo_after_sweep(s, lv, colour, false);
+        launch_half_sweep(lv.g, lv.a[MGB_U].base, lv.a[MGB_D].base, lv.hSq, colour, lo + 1,
+                          hi - 1, s->st);
+        comm_end(s);
+        return;
+    }
+    launch_half_sweep(lv.g, lv.a[MGB_U].base, lv.a[MGB_D].base, lv.hSq, colour, lo, hi, s->st);
     halo_after_sweep(s, lv, colour);
 }
 
@@ -819,22 +1114,24 @@ static void q_residual_restrict(mgb_solver *s, int q, int colour = -1)
         halo_step(s, c, c.a[MGB_D].base, 3, c.own_hi - 1, c.own_lo - 1, -1, -1);
     } else {
         // agglomeration: gather the coarse rhs slabs on rank 0
+        comm_begin(s);
         NC(nccl().GroupStart());
         for (int col = 0; col < 2; col++) {
             double *base = c.a[MGB_D].base + (long long)col * c.g.cs;
             if (s->rank > 0) {
                 NC(nccl().Send(base + (long long)Ilo * c.g.pj, (size_t)(Ihi - Ilo) * c.g.pj,
-                               ncclDouble, 0, s->comm, s->st));
+                               ncclDouble, 0, s->comm, nccl_stream(s)));
             } else {
                 for (int r = 1; r < s->nranks; r++) {
                     int lo, hi;
                     mgb_plan_slab(c.g.ni, s->nranks, r, &lo, &hi);
                     NC(nccl().Recv(base + (long long)lo * c.g.pj, (size_t)(hi - lo) * c.g.pj,
-                                   ncclDouble, r, s->comm, s->st));
+                                   ncclDouble, r, s->comm, nccl_stream(s)));
                 }
             }
         }
         NC(nccl().GroupEnd());
+        comm_end(s);
         s->nccl_calls++;
     }
 }
@@ -854,6 +1151,7 @@ static void q_prolong(mgb_solver *s, int q)
     const int hi = f.own_hi + (s->rank < s->nranks - 1 ? 1 : 0);
     launch_prolong_correct(c.g, c.a[MGB_U].base, f.g, f.a[MGB_U].base, lo - f.g.i0,
                            hi - f.g.i0, s->st);
+    halo_fence(s, f);
 }
 
 // after rank 0 has finished the agglomerated levels: everybody gets the
@@ -861,8 +1159,10 @@ static void q_prolong(mgb_solver *s, int q)
 static void q_broadcast_agglomerated(mgb_solver *s)
 {
     Level &c = s->lv[s->LD - 1];
+    comm_begin(s);
     NC(nccl().Broadcast(c.a[MGB_U].base, c.a[MGB_U].base, (size_t)(2 * c.g.cs), ncclDouble, 0,
-                        s->comm, s->st));
+                        s->comm, nccl_stream(s)));
+    comm_end(s);
     s->nccl_calls++;
 }
 
@@ -1032,8 +1332,10 @@ static void enqueue_cycle(mgb_solver *s, int q, bool timed)
     Level &lv = s->lv[q];
     if (!s->works_on(q))
         return;  // agglomerated levels run on rank 0 only
-    if (q < s->L - 1)  // 1254-1260: coarse levels start from a zero guess
+    if (q < s->L - 1) {  // 1254-1260: coarse levels start from a zero guess
         cudaMemsetAsync(lv.a[MGB_U].base, 0, sizeof(double) * 2 * lv.g.cs, s->st);
+        halo_fence(s, lv);
+    }
     if (q == 0) {  // 1262-1277
         StageTimer t(s, timed, 0, MGB_ST_RECURSE);
         q_coarse_solve(s);
@@ -1158,7 +1460,10 @@ extern "C" int mgb_vcycle(mgb_solver *s, double *sumsq)
             *sumsq = v;
         return 0;
     }
-    if (s->opt_graph) {
+    // a partitioned solver runs its first cycle eagerly: NCCL sets up its
+    // connections on first use, which must not happen inside a capture
+    const bool warm_up = s->is_dist() && s->opt_graph && !s->gexec && s->eager_cycles++ < 1;
+    if (s->opt_graph && !warm_up) {
         if (!s->gexec && build_graph(s))
             return 1;
         CK(cudaGraphLaunch(s->gexec, s->st));

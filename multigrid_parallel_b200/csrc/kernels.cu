@@ -1008,6 +1008,117 @@ void launch_prolong_correct(const Geo &gc, const double *ec, const Geo &gf,
 }
 
 // ----------------------------------------------------------------------------
+// halo exchange over NVLink: P2P stores into the neighbour's halo planes + a
+// sequence-numbered flag (release/acquire at system scope).  One process per
+// GPU, the neighbour's arrays mapped through CUDA IPC.
+// ----------------------------------------------------------------------------
+struct HaloDir {  // one direction of a halo step: up to two runs + the neighbour's flag
+    const double *src[2];
+    double *dst[2];
+    long long n[2];
+    unsigned long long *peer_flag;  // nullptr: nothing goes this way
+    unsigned long long *seq;        // my sequence number for this direction (local)
+    unsigned int *done;             // block counter (local)
+};
+
+__global__ void __launch_bounds__(256) k_halo_push(HaloDir up, HaloDir low)
+{
+    // the first gridDim.x/2 blocks (or all, if only one direction is active)
+    // serve `up`, the rest `low`
+    const bool both = up.peer_flag && low.peer_flag;
+    const unsigned int half = both ? gridDim.x / 2 : gridDim.x;
+    const bool mine_up = up.peer_flag && (!both || blockIdx.x < half);
+    const HaloDir &d = mine_up ? up : low;
+    const unsigned int nb = both ? (mine_up ? half : gridDim.x - half) : gridDim.x;
+    const unsigned int b = both && !mine_up ? blockIdx.x - half : blockIdx.x;
+    const long long stride = (long long)nb * blockDim.x;
+    const long long t0 = (long long)b * blockDim.x + threadIdx.x;
+    // runs start on 16-byte boundaries and have even lengths (colour planes)
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+        const double2 *s = reinterpret_cast<const double2 *>(d.src[k]);
+        double2 *o = reinterpret_cast<double2 *>(d.dst[k]);
+        for (long long t = t0; 2 * t < d.n[k]; t += stride)
+            o[t] = s[t];
+    }
+    __threadfence_system();  // this thread's peer stores are visible system-wide ...
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int prev = atomicAdd(d.done, 1u);
+        if (prev == nb - 1) {  // ... and the last block to get here has seen all of them
+            *d.done = 0;
+            const unsigned long long v = *d.seq + 1;
+            *d.seq = v;
+            __threadfence_system();
+            asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(d.peer_flag), "l"(v)
+                         : "memory");
+        }
+    }
+}
+
+// thread 0 waits for flag0 (if any), thread 1 for flag1 (if any)
+__global__ void k_halo_wait(const unsigned long long *flag0, unsigned long long *expect0,
+                            const unsigned long long *flag1, unsigned long long *expect1)
+{
+    const unsigned long long *flag = threadIdx.x == 0 ? flag0 : flag1;
+    unsigned long long *expect = threadIdx.x == 0 ? expect0 : expect1;
+    if (!flag)
+        return;
+    const unsigned long long v = *expect + 1;
+    *expect = v;
+    const long long t0 = clock64();
+    while (true) {
+        unsigned long long cur;
+        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(cur) : "l"(flag) : "memory");
+        if (cur >= v)
+            break;
+        if (clock64() - t0 > 20000000000LL)  // ~10 s: a lost neighbour must not hang the GPU
+            __trap();
+    }
+}
+
+void launch_halo_push(const HaloRun &up, const HaloRun &low, cudaStream_t st)
+{
+    if (!up.peer_flag && !low.peer_flag)
+        return;
+    HaloDir a{}, b{};
+    long long most = 0;
+    const HaloRun *in[2] = {&up, &low};
+    HaloDir *out[2] = {&a, &b};
+    for (int i = 0; i < 2; i++) {
+        for (int k = 0; k < 2; k++) {
+            out[i]->src[k] = in[i]->src[k];
+            out[i]->dst[k] = in[i]->dst[k];
+            out[i]->n[k] = in[i]->n[k];
+            if (in[i]->peer_flag && in[i]->n[k] > most)
+                most = in[i]->n[k];
+        }
+        out[i]->peer_flag = in[i]->peer_flag;
+        out[i]->seq = in[i]->seq;
+        out[i]->done = in[i]->done;
+    }
+    long long nb = (most / 2 + 256 * 8 - 1) / (256 * 8);  // ~8 x 16 B per thread and direction
+    if (nb > 64)
+        nb = 64;
+    if (nb < 1)
+        nb = 1;
+    if (up.peer_flag && low.peer_flag)
+        nb *= 2;
+    k_halo_push<<<(unsigned)nb, 256, 0, st>>>(a, b);
+    COUNT_LAUNCH();
+}
+
+void launch_halo_wait(const unsigned long long *flag0, unsigned long long *expect0,
+                      const unsigned long long *flag1, unsigned long long *expect1,
+                      cudaStream_t st)
+{
+    if (!flag0 && !flag1)
+        return;
+    k_halo_wait<<<1, 2, 0, st>>>(flag0, expect0, flag1, expect1);
+    COUNT_LAUNCH();
+}
+
+// ----------------------------------------------------------------------------
 // reductions over whole arrays
 // ----------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)

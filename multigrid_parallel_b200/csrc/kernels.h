@@ -67,6 +67,26 @@ bool launch_tile_residual_restrict(const Geo &gf, double *vf, const double *df, 
                                    double invHsq, int colour, const Geo &gc, double *dc,
                                    int Il_lo, int Il_hi, cudaStream_t st);
 
+// ---- halo exchange over NVLink peer memory (kernels.cu) ----
+// push: copy up to two contiguous runs of doubles into the neighbour GPU's
+// memory (IPC-mapped peer pointers), then -- once every block's stores are
+// fenced system-wide -- bump this direction's sequence number (*seq, local) and
+// release it into the neighbour's flag.  wait: spin (one thread) until the
+// local flag reaches the next expected sequence number (*expect, local).
+struct HaloRun {  // one direction: up to two contiguous runs (colours) + where to signal
+    const double *src[2] = {nullptr, nullptr};
+    double *dst[2] = {nullptr, nullptr};
+    long long n[2] = {0, 0};
+    unsigned long long *peer_flag = nullptr;  // nullptr: nothing goes this way
+    unsigned long long *seq = nullptr;
+    unsigned int *done = nullptr;
+};
+// both directions in ONE launch, both waits in ONE launch
+void launch_halo_push(const HaloRun &up, const HaloRun &low, cudaStream_t st);
+void launch_halo_wait(const unsigned long long *flag0, unsigned long long *expect0,
+                      const unsigned long long *flag1, unsigned long long *expect1,
+                      cudaStream_t st);
+
 // dense coarse operator + LU (mg_3d.h:147-273, gauss_elim.h:9-60)
 void launch_coarse_matrix(double *A, int ni, int nj, int nk, double h,
                           cudaStream_t st);

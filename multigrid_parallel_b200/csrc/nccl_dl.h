@@ -21,6 +21,8 @@ struct NcclApi {
                               cudaStream_t) = nullptr;
     ncclResult_t (*Broadcast)(const void *, void *, size_t, ncclDataType_t, int, ncclComm_t,
                               cudaStream_t) = nullptr;
+    ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t,
+                              cudaStream_t) = nullptr;
     const char *error = nullptr;
 
     bool load()
@@ -53,6 +55,7 @@ struct NcclApi {
         MGB_SYM(Recv, "ncclRecv")
         MGB_SYM(AllReduce, "ncclAllReduce")
         MGB_SYM(Broadcast, "ncclBroadcast")
+        MGB_SYM(AllGather, "ncclAllGather")
 #undef MGB_SYM
         return true;
     }

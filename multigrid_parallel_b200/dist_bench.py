@@ -19,8 +19,12 @@ def run(args, rank, world, local_rank):
     from multigrid_parallel_b200 import dist as D
 
     D.init_process_group("gloo")
-    coarse = (2 * world + 1, 3, 3)
-    s = D.make_solver(coarse, LEVELS, GS)
+    strong = getattr(args, "problem", "weak") == "strong1025"
+    # weak: 513^3 per GPU (config 5's shape); strong: the SAME 1025^3 cube on any
+    # number of GPUs (BASELINE config 4), 10 levels
+    coarse = (3, 3, 3) if strong else (2 * world + 1, 3, 3)
+    levels = 10 if strong else LEVELS
+    s = D.make_solver(coarse, levels, GS)
     top = s.levels - 1
     ni, nj, nk = s.dims(top)
     dof = float(ni) * nj * nk
@@ -55,6 +59,42 @@ def run(args, rank, world, local_rank):
     clocks = sampler.finish() if sampler else None
     value = dof * args.steps / dt
 
+    if strong:
+        fresh()
+        hist = s.solve(init * TOL, 100)
+        import os
+        if os.environ.get("MGB_BENCH_STAGES"):
+            # per level and stage device times (CUDA events) of rank 0 and the last rank
+            from multigrid_parallel_b200.solver import OPT_PROFILE
+            s.set_option(OPT_PROFILE, 1)
+            s.vcycle()
+            s.timing_reset()
+            for _ in range(3):
+                s.vcycle()
+            if rank in (0, world - 1):
+                for lvl in range(s.levels - 1, -1, -1):
+                    row = " ".join(f"{s.timing(lvl, st)[1] / 3 * 1e6:9.1f}" for st in range(7))
+                    print(f"[rank {rank}] L{lvl} us/cycle: {row}", flush=True)
+            s.set_option(OPT_PROFILE, 0)
+        if rank == 0:
+            print(json.dumps({
+                "metric": "vcycle_dof_per_s", "value": value, "unit": "DOF*cycles/s",
+                "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+                "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
+                "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": f"{ni}x{nj}x{nk} fp64 Laplace V(2,2)-cycle, coarse 3^3 LU, "
+                                       f"{levels} levels (BASELINE config 4: strong scaling)",
+                           "parallelism": f"i-slabs over {world} GPUs, NCCL halo exchange per "
+                                          f"half-sweep, levels < {s.first_dist_level} on rank 0"
+                                          if world > 1 else "single GPU",
+                           "l2": "inputs larger than L2", "cycles_to_1e-8": len(hist),
+                           "final_residual": float(hist[-1])},
+                "clocks": clocks, "gpu_launches": int(launches), "e2e": None, "roofline": None,
+                "cpu_baseline": None}), flush=True)
+        D.barrier()
+        s.close()
+        return 0
+
     # end to end: every rank uploads its slab from pinned host memory, the
     # ranks solve to 1e-8*||d|| together, every rank downloads its slab
     shape = s.local_shape(top)
@@ -85,7 +125,7 @@ def run(args, rank, world, local_rank):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
             "config": {"workload": f"{ni}x{nj}x{nk} fp64 Laplace V(2,2)-cycle (513^3 per-GPU slab "
-                                   f"stretched along i), coarse {coarse[0]}x3x3 LU, {LEVELS} levels",
+                                   f"stretched along i), coarse {coarse[0]}x3x3 LU, {levels} levels",
                        "parallelism": f"i-slabs over {world} GPUs, NCCL halo exchange per half-sweep, "
                                       f"levels < {s.first_dist_level} agglomerated on rank 0",
                        "l2": "inputs larger than L2", "cycles_to_1e-8": cycles,

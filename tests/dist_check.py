@@ -80,13 +80,15 @@ def main():
         ((5, 3, 5), 5, 3, 4, 0, 2, True),
         ((3, 3, 3), 8, 2, 16, -1, 2, False),     # 257^3 with the default thresholds
     ]
-    for case in cases:
-        if (case[0][0] - 1) * 2 % world:
-            continue
-        info = check_case(*case, rank, world, local_rank)
-        D.barrier()
-        if rank == 0:
-            print("ok", info, flush=True)
+    for min_plane in (40000, 0):  # default kernel choice, then TMA tile kernels on every level
+        m.set_global(m.G_TILE_MIN_PLANE, min_plane)
+        for case in cases:
+            if (case[0][0] - 1) * 2 % world:
+                continue
+            info = check_case(*case, rank, world, local_rank)
+            D.barrier()
+            if rank == 0:
+                print("ok", info, "tile_min_plane", min_plane, flush=True)
     print(f"DIST_CHECK_OK rank {rank}/{world}", flush=True)
 
 

@@ -1,4 +1,5 @@
-set -x
-python bench.py > gpurun_out/bench_r01b.log 2>&1; tail -1 gpurun_out/bench_r01b.log
-python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref_r01b.log 2>&1; tail -1 gpurun_out/bench_ref_r01b.log
-python tools/probe.py --levels 9 --reps 2 --cycles 1 > gpurun_out/probe_plain_r01b.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:"k_half_sweep|k_tile|k_prolong_correct8" -c 10 -o gpurun_out/prof_r01b python tools/probe.py --levels 9 --reps 2 --cycles 1 > gpurun_out/ncu_r01b.log 2>&1
+run() { env "$@" timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29518 bench.py "${ARGS[@]}" 2>&1 | grep -E "metric" | tail -1; }
+ARGS=(--problem strong1025 --gpus 8 --steps 10 --warmup 3)
+echo "strong p2p graph"; run A=1 | tee gpurun_out/strong8_p2p_graph.log | cut -c1-220
+ARGS=(--gpus 8 --steps 10 --warmup 3)
+echo "weak p2p graph"; run A=1 | tee gpurun_out/weak8_p2p_graph.log | cut -c1-220
