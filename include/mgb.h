@@ -42,7 +42,8 @@ enum {                                             /* mgb_set_option keys */
     MGB_OPT_FUSE = 2,       /* 0: every stage its own kernel, r stored; 1 (default): fused
                              * residual+restriction, r not stored; 2: also the last colour
                              * of each smoother leg inside the residual kernel that follows */
-    MGB_OPT_GRAPH_LEVELS = 3/* only levels < this are graphed when PROFILE=1               */
+    MGB_OPT_GRAPH_LEVELS = 3,/* only levels < this are graphed when PROFILE=1              */
+    MGB_OPT_TAIL = 4        /* 1 (default): the levels of <= ~17^3 points run as ONE kernel */
 };
 
 /* ---- errors / device ---------------------------------------------------- */

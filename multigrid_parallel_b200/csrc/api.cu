@@ -138,6 +138,8 @@ struct mgb_solver {
     double *lu = nullptr, *lut = nullptr, *cb = nullptr, *cx = nullptr;
     // options
     int opt_graph = 1, opt_profile = 0, opt_fuse = 1;
+    // levels 0..tail_top (<= ~33^3) run as ONE kernel (tail.cu); -1: none
+    int opt_tail = 1, tail_top = -1;
     cudaGraphExec_t gexec = nullptr;
     long long graph_launches = 0;
     int eager_cycles = 0;  // partitioned solver: cycles run eagerly before the capture
@@ -519,6 +521,23 @@ static int create_impl(mgb_solver **out, int ci, int cj, int ck, int levels, int
                 return 1;
             }
     }
+    {
+        // deepest run of small, unpartitioned levels: one kernel does them all
+        // (one SM hides L2 latency for <= 17^3 points per level; at 33^3 the
+        // per-stage kernels spread over the GPU are faster again -- measured)
+        const long long max_pts = getenv("MGB_TAIL_POINTS") ? atoll(getenv("MGB_TAIL_POINTS")) : 5000;
+        if (getenv("MGB_TAIL"))
+            s->opt_tail = atoi(getenv("MGB_TAIL")) != 0;
+        const int lim = nranks > 1 ? s->LD - 1 : levels - 2;  // strictly coarse, on one GPU
+        for (int l = 0; l <= lim && l < 8; l++) {
+            const Geo &g = s->lv[l].g;
+            if ((long long)g.ni * g.nj * g.nk > max_pts)
+                break;
+            s->tail_top = l;
+        }
+        if ((long long)ci * cj * ck > 1024)
+            s->tail_top = -1;
+    }
     s->secs.assign((size_t)levels * MGB_NUM_STAGES, 0.);
     s->calls.assign((size_t)levels * MGB_NUM_STAGES, 0);
 
@@ -682,6 +701,10 @@ extern "C" int mgb_set_option(mgb_solver *s, int key, int value)
         drop_graph(s);
         break;
     case MGB_OPT_GRAPH_LEVELS: break;
+    case MGB_OPT_TAIL:
+        s->opt_tail = value != 0;
+        drop_graph(s);
+        break;
     default: return fail("unknown option %d", key);
     }
     return 0;
@@ -1332,6 +1355,24 @@ static void enqueue_cycle(mgb_solver *s, int q, bool timed)
     Level &lv = s->lv[q];
     if (!s->works_on(q))
         return;  // agglomerated levels run on rank 0 only
+    if (q == s->tail_top && s->opt_tail && !timed && s->lu) {
+        // levels q .. 0 .. q in one single-block kernel (tail.cu); the stage timers
+        // of MGB_OPT_PROFILE keep the per-stage kernels
+        TailP p{};
+        p.top = q;
+        p.gs = s->gs;
+        p.zero_top = 1;
+        p.nc = s->nc;
+        p.lu = s->lu;
+        p.lut = s->lut;
+        for (int l = 0; l <= q; l++) {
+            Level &t = s->lv[l];
+            p.lv[l] = TailLevel{t.g, t.a[MGB_U].base, t.a[MGB_D].base, t.a[MGB_R].base, t.hSq,
+                                t.invHsq};
+        }
+        launch_coarse_tail(p, s->st);
+        return;
+    }
     if (q < s->L - 1) {  // 1254-1260: coarse levels start from a zero guess
         cudaMemsetAsync(lv.a[MGB_U].base, 0, sizeof(double) * 2 * lv.g.cs, s->st);
         halo_fence(s, lv);

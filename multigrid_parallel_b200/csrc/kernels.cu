@@ -11,6 +11,7 @@
 #include <cstdlib>
 
 #include "kernels.h"
+#include "devmath.cuh"
 
 namespace mgb {
 
@@ -31,34 +32,6 @@ __device__ __forceinline__ void st2(double *p, double a, double b)
     *reinterpret_cast<double2 *>(p) = make_double2(a, b);
 }
 
-// mg_3d.h:437-442: multFact*(v[p-NN]+v[p+NN]+v[p-N]+v[p+N]+v[p-1]+v[p+1]-hSq*d[p])
-__device__ __forceinline__ double gs_point(double im, double ip, double jm,
-                                           double jp, double km, double kp,
-                                           double hSq, double d, double sixth)
-{
-    double s = __dadd_rn(im, ip);
-    s = __dadd_rn(s, jm);
-    s = __dadd_rn(s, jp);
-    s = __dadd_rn(s, km);
-    s = __dadd_rn(s, kp);
-    s = __dsub_rn(s, __dmul_rn(hSq, d));
-    return __dmul_rn(sixth, s);
-}
-
-// mg_3d.h:818-820: d[p] - invHsq*(v[p-NN]+v[p+NN]+v[p-N]+v[p+N]+v[p-1]+v[p+1]-6*v[p])
-__device__ __forceinline__ double res_point(double im, double ip, double jm,
-                                            double jp, double km, double kp,
-                                            double vc, double d, double invHsq)
-{
-    double s = __dadd_rn(im, ip);
-    s = __dadd_rn(s, jm);
-    s = __dadd_rn(s, jp);
-    s = __dadd_rn(s, km);
-    s = __dadd_rn(s, kp);
-    s = __dsub_rn(s, __dmul_rn(6.0, vc));
-    return __dsub_rn(d, __dmul_rn(invHsq, s));
-}
-
 // mg_3d.h:89-90: x*x - 2*y*y + z*z
 __device__ __forceinline__ double bc_func(double x, double y, double z)
 {
@@ -66,14 +39,6 @@ __device__ __forceinline__ double bc_func(double x, double y, double z)
     double b = __dmul_rn(__dmul_rn(2.0, y), y);
     double c = __dmul_rn(z, z);
     return __dadd_rn(__dsub_rn(a, b), c);
-}
-
-// value of a colour-split array at local plane il, row j, column k
-__device__ __forceinline__ double rd_split(const Geo &g, const double *a, int il,
-                                           int j, int k)
-{
-    const int c = (g.i0 + il + j + k) & 1;
-    return a[c * g.cs + ((long long)il * g.nj + j) * g.kh + (k >> 1)];
 }
 
 // deterministic block sum (blockDim.x multiple of 32, <= 1024); result valid
@@ -264,7 +229,9 @@ static MarchCfg march_cfg(const Geo &g, int nplanes, int threads, int sm_blocks)
     MarchCfg c;
     const long long pairs = (long long)g.pj / 2;
     const unsigned bx = (unsigned)((pairs + threads - 1) / threads);
-    const int nch = pick_chunks(bx, nplanes, sm_blocks);
+    static const int chunk_env = getenv("MGB_MARCH_CHUNK") ? atoi(getenv("MGB_MARCH_CHUNK")) : 0;
+    const int nch = chunk_env > 0 ? (nplanes + chunk_env - 1) / chunk_env
+                                  : pick_chunks(bx, nplanes, sm_blocks);
     c.chunk = (nplanes + nch - 1) / nch;
     const unsigned by = (unsigned)((nplanes + c.chunk - 1) / c.chunk);
     c.grid = dim3(bx, by, 1);
@@ -335,11 +302,102 @@ k_half_sweep(Geo g, const double *__restrict__ vo, double *__restrict__ vc,
     }
 }
 
+// The same half-sweep, software-pipelined: the two DRAM streams of plane il+1
+// (the thread's own pair of the other colour and of the rhs) are requested
+// before plane il is computed, into a second register set (the plane loop is
+// unrolled by two so that no in-flight value is ever copied).  Twice the bytes
+// in flight per thread; the j+-1 rows and the k neighbour still come through
+// L1/L2 at the point of use.
+template <int COLOUR>
+__global__ void __launch_bounds__(256)
+k_half_sweep_pipe(Geo g, const double *__restrict__ vo, double *__restrict__ vc,
+                  const double *__restrict__ dc, double hSq, int il_lo, int il_hi, int chunk)
+{
+    const int npair = g.kh >> 1;
+    const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= (g.pj >> 1))
+        return;
+    const int j = (int)(q / npair);
+    if (j < 1 || j > g.nj - 2)
+        return;
+    const int mp = (int)(q - (long long)j * npair);
+    const int ia = il_lo + blockIdx.y * chunk;
+    const int ib = min(ia + chunk, il_hi);
+    if (ia >= ib)
+        return;
+    const long long off = 2 * q;
+    const double sixth = 1. / 6;
+    const int kh = g.kh;
+    const int kmax = g.nk - 2;
+    const long long pj = g.pj;
+
+    const double *po = vo + (long long)ia * pj + off;  // own pair, other colour, plane il
+    const double *pd = dc + (long long)ia * pj + off;  // rhs of this colour, plane il
+    double *pc = vc + (long long)ia * pj + off;
+    double2 bot = ld2(po - pj);
+    double2 mid = ld2(po);
+    struct Pre { double2 top, dd; };
+    Pre A, B;
+    A.top = ld2(po + pj);
+    A.dd = ld2(pd);
+    B = A;
+    int kp = (COLOUR ^ (g.i0 + ia + j)) & 1;
+    int il = ia;
+    auto step = [&](const Pre &cur, Pre &nxt) {
+        if (il + 1 < ib) {
+            nxt.top = ld2(po + 2 * pj);
+            nxt.dd = ld2(pd + pj);
+        }
+        const double2 jm = ld2(po - kh);
+        const double2 jp = ld2(po + kh);
+        double a0, a1, a2;
+        if (kp) {
+            a0 = mid.x; a1 = mid.y; a2 = po[2];
+        } else {
+            a0 = po[-1]; a1 = mid.x; a2 = mid.y;
+        }
+        const double r0 = gs_point(bot.x, cur.top.x, jm.x, jp.x, a0, a1, hSq, cur.dd.x, sixth);
+        const double r1 = gs_point(bot.y, cur.top.y, jm.y, jp.y, a1, a2, hSq, cur.dd.y, sixth);
+        const int k0 = 4 * mp + kp, k1 = k0 + 2;
+        const bool ok0 = k0 >= 1 && k0 <= kmax;
+        const bool ok1 = k1 <= kmax;  // k1 >= 2 always
+        if (ok0 && ok1)
+            st2(pc, r0, r1);
+        else if (ok0)
+            pc[0] = r0;
+        else if (ok1)
+            pc[1] = r1;
+        bot = mid;
+        mid = cur.top;  // already consumed above: the copy does not wait
+        po += pj; pd += pj; pc += pj;
+        kp ^= 1;
+        il++;
+    };
+    while (il < ib) {
+        step(A, B);
+        if (il < ib)
+            step(B, A);
+    }
+}
+
 void launch_half_sweep(const Geo &g, double *v, const double *d, double hSq,
                        int colour, int il_lo, int il_hi, cudaStream_t st)
 {
     if (il_hi <= il_lo)
         return;
+    static const int pipe = getenv("MGB_SWEEP_PIPE") ? atoi(getenv("MGB_SWEEP_PIPE")) : 1;
+    if (pipe) {
+        static const int occp = resident_blocks(k_half_sweep_pipe<1>, 256, 0);
+        const MarchCfg c = march_cfg(g, il_hi - il_lo, 256, occp);
+        if (colour)
+            k_half_sweep_pipe<1><<<c.grid, c.block, 0, st>>>(g, v, v + g.cs, d + g.cs, hSq, il_lo,
+                                                             il_hi, c.chunk);
+        else
+            k_half_sweep_pipe<0><<<c.grid, c.block, 0, st>>>(g, v + g.cs, v, d, hSq, il_lo, il_hi,
+                                                             c.chunk);
+        COUNT_LAUNCH();
+        return;
+    }
     static const int occ = resident_blocks(k_half_sweep<1>, 256, 0);
     const MarchCfg c = march_cfg(g, il_hi - il_lo, 256, occ);
     if (colour)
@@ -730,55 +788,6 @@ __device__ __forceinline__ C3 ld_c3(const Geo &gc, const double *__restrict__ ec
     r.y = e1[mp];
     r.z = e0[mp + 1];
     return r;
-}
-
-__device__ __forceinline__ double add0(double x) { return __dadd_rn(0., x); }
-
-// fine point with even k on coarse column x (ok = 0)
-__device__ __forceinline__ double pc_even(int oi, int oj, double a0, double a1, double b0,
-                                          double b1)
-{
-    if (!oi && !oj)
-        return a0;  // 1137-1138
-    if (oi && !oj)
-        return __dmul_rn(__dadd_rn(add0(a0), b0), 0.5);  // 1105-1111
-    if (!oi)
-        return __dmul_rn(__dadd_rn(add0(a0), a1), 0.5);  // 1112-1118
-    // 1080-1089: j fastest, then i
-    double t = __dadd_rn(add0(a0), a1);
-    t = __dadd_rn(t, b0);
-    t = __dadd_rn(t, b1);
-    return __dmul_rn(t, 0.25);
-}
-
-// fine point with odd k between coarse columns x (low) and y (high) (ok = 1)
-__device__ __forceinline__ double pc_odd(int oi, int oj, double a0x, double a0y, double a1x,
-                                         double a1y, double b0x, double b0y, double b1x,
-                                         double b1y)
-{
-    if (!oi && !oj)
-        return __dmul_rn(__dadd_rn(add0(a0x), a0y), 0.5);  // 1119-1125
-    if (oi && !oj) {  // 1070-1079: i fastest, then k
-        double t = __dadd_rn(add0(a0x), b0x);
-        t = __dadd_rn(t, a0y);
-        t = __dadd_rn(t, b0y);
-        return __dmul_rn(t, 0.25);
-    }
-    if (!oi) {  // 1059-1068: j fastest, then k
-        double t = __dadd_rn(add0(a0x), a1x);
-        t = __dadd_rn(t, a0y);
-        t = __dadd_rn(t, a1y);
-        return __dmul_rn(t, 0.25);
-    }
-    // 1023-1049: i-major, then j, then k
-    double t = __dadd_rn(add0(a0x), a0y);
-    t = __dadd_rn(t, a1x);
-    t = __dadd_rn(t, a1y);
-    t = __dadd_rn(t, b0x);
-    t = __dadd_rn(t, b0y);
-    t = __dadd_rn(t, b1x);
-    t = __dadd_rn(t, b1y);
-    return __dmul_rn(t, 0.125);
 }
 
 __global__ void __launch_bounds__(256)

@@ -87,6 +87,22 @@ void launch_halo_wait(const unsigned long long *flag0, unsigned long long *expec
                       const unsigned long long *flag1, unsigned long long *expect1,
                       cudaStream_t st);
 
+// ---- the deep coarse levels as one single-block kernel (tail.cu) ----
+struct TailLevel {
+    Geo g;
+    double *u, *d, *r;
+    double hSq, invHsq;
+};
+struct TailP {
+    int top;          // levels top .. 0 .. top are done in the kernel
+    int gs;           // smoothing iterations per leg
+    int zero_top;     // level `top` starts from a zero guess (it is a coarse level)
+    int nc;           // unknowns of level 0 (<= 1024)
+    const double *lu, *lut;
+    TailLevel lv[8];
+};
+void launch_coarse_tail(const TailP &p, cudaStream_t st);
+
 // dense coarse operator + LU (mg_3d.h:147-273, gauss_elim.h:9-60)
 void launch_coarse_matrix(double *A, int ni, int nj, int nk, double h,
                           cudaStream_t st);

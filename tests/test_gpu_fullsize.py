@@ -14,7 +14,8 @@ Measured deviation of the reference's own one-thread sum from the exact one:
 1-thread and 8-thread norms differ from each other by 6.5e-10 (first cycle:
 golden 309102136.013 vs SURVEY Appendix A 309102136.214).  Hence, against the
 reference's PRINTED norms: 1e-12 up to 65^3, 1e-11 at 129^3, 5e-11 at 257^3,
-5e-10 at 513^3, 2e-9 at 1025^3 -- and against "history_exact" (the reference's
+5e-10 at 513^3, 1e-8 at 1025^3 (measured 2.6e-9: the sequential sum's error
+grows like the number of points) -- and against "history_exact" (the reference's
 own residual field after every cycle, summed in long double by
 oracle/gen_exact_history.py) 1e-13 at every size that has it."""
 import hashlib
@@ -48,7 +49,7 @@ def _solve(mgb, g, **opts):
 @pytest.mark.parametrize("key,rtol", [("3_5_2", 1e-12), ("3_5_1", 1e-12), ("3_5_3", 1e-12),
                                       ("5_4_2", 1e-12), ("9_3_2", 1e-12), ("3_6_2", 1e-12),
                                       ("3_7_2", 1e-11), ("3_8_2", 5e-11), ("3_9_2", 5e-10),
-                                      ("3_10_2", 2e-9)])
+                                      ("3_10_2", 1e-8)])
 def test_solve_matches_reference_golden(mgb, histories, key, rtol):
     if key not in histories:
         pytest.skip(f"golden {key} not generated (oracle/gen_golden.py --huge)")
@@ -143,3 +144,20 @@ def test_fixed_point_is_idempotent(mgb):
         assert s.residual(top) < 1e-6 * math.sqrt(N ** 3) / h ** 2 * 1e-9
         s.smooth(top, 2, True)
         assert np.max(np.abs(s.download(top, mgb.MGB_U) - exact)) < 1e-14
+
+
+def test_rb_gs_flow_257_matches_reference(mgb):
+    """BASELINE config 2 (test_rb_gs_3d.c:56-101 flow, d == 0, 257^3): residual
+    norms after iterations 1..5 and 10 as produced by the reference (SURVEY.md
+    Appendix A, one thread; 8 threads agree to 1e-13)"""
+    want = {0: 39429263.432111837, 1: 26202730.587062154, 2: 18704743.16078392,
+            3: 14819928.628106939, 4: 12409130.770850345, 5: 10750238.124142876,
+            10: 6718454.1814461211}
+    with mgb.Solver(257, 1, 1) as s:
+        s.set_dirichlet(0, mgb.MGB_U)
+        assert s.residual(0) == pytest.approx(want[0], rel=1e-11)
+        for it in range(1, 11):
+            s.smooth(0, 1, True)    # preSmoother(v, d, N, h, 1)
+            s.smooth(0, 1, False)   # postSmoother(v, d, N, h, 1)
+            if it in want:
+                assert s.residual(0) == pytest.approx(want[it], rel=1e-11), it

@@ -284,11 +284,11 @@ def test_stateless_transfer_operators(mgb, orc):
 
 
 @pytest.mark.parametrize("coarse,levels,gs", [((3, 3, 3), 5, 2), ((5, 5, 5), 3, 1), ((3, 5, 9), 4, 3)])
-@pytest.mark.parametrize("mode", ["graph", "eager", "profile", "unfused", "fuse1", "fuse2"])
+@pytest.mark.parametrize("mode", ["graph", "eager", "profile", "unfused", "fuse1", "fuse2", "notail"])
 def test_vcycle_bitwise_all_levels(mgb, orc, coarse, levels, gs, mode):
     """one and several V-cycles: every level's u and d match the oracle bit
     for bit, the returned norm to 1e-13"""
-    from multigrid_parallel_b200.solver import OPT_FUSE, OPT_GRAPH, OPT_PROFILE
+    from multigrid_parallel_b200.solver import OPT_FUSE, OPT_GRAPH, OPT_PROFILE, OPT_TAIL
     mg = OrcMG(orc, coarse, levels, gs)
     with _mk(mgb, coarse, levels, gs) as s:
         if mode == "eager":
@@ -301,6 +301,8 @@ def test_vcycle_bitwise_all_levels(mgb, orc, coarse, levels, gs, mode):
             s.set_option(OPT_FUSE, 1)
         elif mode == "fuse2":
             s.set_option(OPT_FUSE, 2)
+        elif mode == "notail":
+            s.set_option(OPT_TAIL, 0)
         top = levels - 1
         u0, d0 = seeded(s.dims(top), 41), seeded(s.dims(top), 42)
         mg.u(top)[...] = u0
