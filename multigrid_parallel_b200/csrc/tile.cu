@@ -354,12 +354,12 @@ k_tile(const TileP P, const __grid_constant__ CUtensorMap tm_v,
     // phase B of a RESTRICT step: the coarse threads add plane t's nine products
     // to their open sum; an odd plane closes coarse plane I and opens I+1 with
     // the same products (mg_3d.h:980-989, ti-major order)
-    auto accumulate = [&](int t) {
+    auto accumulate = [&](int t, int xo) {
         if (cthr) {
             const int ig = g.i0 + t;
             const bool odd = ig & 1;
             const double wf = odd ? 0.5 : 1.0;  // ti = 0/2 vs ti = 1
-            const double *x = xr + xoff;
+            const double *x = xr + xo;
             double a = cacc, sfresh = 0.;
 #pragma unroll
             for (int tj = 0; tj < 3; tj++, x += TQt) {
@@ -386,7 +386,6 @@ k_tile(const TileP P, const __grid_constant__ CUtensorMap tm_v,
                 cacc = a;
             }
         }
-        xoff ^= 4 * pl;
     };
     auto put_residuals = [&](double n0, double n1, double n2, double n3, bool counted) {
         if (RESTRICT) {
@@ -412,78 +411,83 @@ k_tile(const TileP P, const __grid_constant__ CUtensorMap tm_v,
         // =====================================================================
         // residual only: both colours of the solution come from the ring
         // =====================================================================
-        struct Pre { double2 d0, d1; };
+        // Registers are kept by k-PARITY, not by colour: E = the quad's even-k
+        // entries (k = 4q, 4q+2), O = its odd-k entries (4q+1, 4q+3).  Which
+        // colour array holds E flips with the row parity s = (i+j)&1 (E lives in
+        // colour s), so the flip is a pointer offset, never a register shuffle.
+        struct Pre { double2 dE, dO; };
         wait_next();  // plane ia-1 (slot 0)
         wait_next();  // plane ia   (slot 1)
-        double2 bot0 = z2, mid0 = z2, bot1 = z2, mid1 = z2;
-        Pre A{z2, z2}, B{z2, z2};
         const int col1 = RS * PW;  // colour 1 inside a slot
-        const double *q_cur = ring + slot_d + so;  // own pair, plane t
+        int s = (g.i0 + ia + j) & 1;                 // row parity on plane t
+        int offE = s ? col1 : 0, offO = col1 - offE;  // slot offsets of the E / O colour on plane t
+        long long dE_off = s ? g.cs : 0;              // ... and in the rhs array
+        double2 botE = z2, midE = z2, botO = z2, midO = z2;
+        Pre A{z2, z2}, B{z2, z2};
+        const double *q_cur = ring + slot_d + so;  // own pair, plane t, colour 0
         int n_s = 2;                                // slot of plane t+1
         if (live) {
-            const double *sa = ring + so;
-            bot0 = ld2(sa); bot1 = ld2(sa + col1);
-            mid0 = ld2(q_cur); mid1 = ld2(q_cur + col1);
+            const double *sa = ring + so;  // plane ia-1: parities swapped
+            botE = ld2(sa + offO); botO = ld2(sa + offE);
+            midE = ld2(q_cur + offE); midO = ld2(q_cur + offO);
         }
         const double *pd = P.d + (long long)ia * g.pj + offq;  // rhs colour 0, plane t
         if (calc) {
-            A.d0 = ld2(pd);
-            A.d1 = ld2(pd + g.cs);
+            A.dE = ld2(pd + dE_off);
+            A.dO = ld2(pd + (g.cs - dE_off));
         }
-        int s = (g.i0 + ia + j) & 1;  // row parity on plane t
+        const bool mE0 = fk & 1, mE1 = fk & 2, mO0 = fk & 4, mO1 = fk & 8;
         auto step = [&](int t, const Pre &cur, Pre &nxt) {
             wait_next();  // plane t+1
             const double *q_nxt = ring + n_s * slot_d + so;
             double n0 = 0., n1 = 0., n2 = 0., n3 = 0.;
             pd += g.pj;
             if (live) {
-                const double2 top0 = ld2(q_nxt), top1 = ld2(q_nxt + col1);
+                // on plane t+1 the parities swap colours
+                const double2 topE = ld2(q_nxt + offO), topO = ld2(q_nxt + offE);
                 if (calc) {
                     if (t + 1 < ib) {
-                        nxt.d0 = ld2(pd);
-                        nxt.d1 = ld2(pd + g.cs);
+                        nxt.dE = ld2(pd + (g.cs - dE_off));
+                        nxt.dO = ld2(pd + dE_off);
                     }
-                    const double *p0 = q_cur, *p1 = q_cur + col1;
-                    const double2 jm0 = ld2(p0 - PW), jp0 = ld2(p0 + PW);
-                    const double2 jm1 = ld2(p1 - PW), jp1 = ld2(p1 + PW);
-                    double b0, b1, b2, c0_, c1_, c2_;
-                    if (s) {
-                        b0 = mid1.x; b1 = mid1.y; b2 = p1[2];
-                        c0_ = p0[-1]; c1_ = mid0.x; c2_ = mid0.y;
-                    } else {
-                        b0 = p1[-1]; b1 = mid1.x; b2 = mid1.y;
-                        c0_ = mid0.x; c1_ = mid0.y; c2_ = p0[2];
-                    }
-                    double rb0 = res_point(bot1.x, top1.x, jm1.x, jp1.x, b0, b1, mid0.x, cur.d0.x, invHsq);
-                    double rb1 = res_point(bot1.y, top1.y, jm1.y, jp1.y, b1, b2, mid0.y, cur.d0.y, invHsq);
-                    double rr0 = res_point(bot0.x, top0.x, jm0.x, jp0.x, c0_, c1_, mid1.x, cur.d1.x, invHsq);
-                    double rr1 = res_point(bot0.y, top0.y, jm0.y, jp0.y, c1_, c2_, mid1.y, cur.d1.y, invHsq);
-                    // colour 0 sits at k offset s, colour 1 at s^1
-                    const int m0 = fk >> (2 * s), m1 = fk >> (2 * (s ^ 1));
-                    if (!(m0 & 1)) rb0 = 0.;
-                    if (!(m0 & 2)) rb1 = 0.;
-                    if (!(m1 & 1)) rr0 = 0.;
-                    if (!(m1 & 2)) rr1 = 0.;
-                    if (s) { n0 = rr0; n1 = rb0; n2 = rr1; n3 = rb1; }
-                    else   { n0 = rb0; n1 = rr0; n2 = rb1; n3 = rr1; }
+                    const double *pE = q_cur + offE, *pO = q_cur + offO;
+                    // rows j+-1 have the other parity: the even-k neighbours of E
+                    // points sit in the O colour's array there, and vice versa
+                    const double2 jmE = ld2(pO - PW), jpE = ld2(pO + PW);
+                    const double2 jmO = ld2(pE - PW), jpO = ld2(pE + PW);
+                    double rE0 = res_point(botE.x, topE.x, jmE.x, jpE.x, pO[-1], midO.x, midE.x, cur.dE.x, invHsq);
+                    double rE1 = res_point(botE.y, topE.y, jmE.y, jpE.y, midO.x, midO.y, midE.y, cur.dE.y, invHsq);
+                    double rO0 = res_point(botO.x, topO.x, jmO.x, jpO.x, midE.x, midE.y, midO.x, cur.dO.x, invHsq);
+                    double rO1 = res_point(botO.y, topO.y, jmO.y, jpO.y, midE.y, pE[2], midO.y, cur.dO.y, invHsq);
+                    n0 = mE0 ? rE0 : 0.;
+                    n1 = mO0 ? rO0 : 0.;
+                    n2 = mE1 ? rE1 : 0.;
+                    n3 = mO1 ? rO1 : 0.;
                 }
-                bot0 = mid0; mid0 = top0;
-                bot1 = mid1; mid1 = top1;
+                botE = midE; midE = topE;
+                botO = midO; midO = topO;
                 put_residuals(n0, n1, n2, n3, true);
             }
+            // the restriction of plane t-1 rides in the same barrier interval as the
+            // residuals of plane t (other buffer): its dependent add chain overlaps
+            // with independent work instead of standing alone behind a barrier
+            if (RESTRICT && t > ia)
+                accumulate(t - 1, xoff ^ (4 * pl));
             q_cur = q_nxt;
             n_s = n_s + 1 == S ? 0 : n_s + 1;
-            s ^= 1;
+            offE = offO; offO = col1 - offE;
+            dE_off = g.cs - dE_off;
+            xoff ^= 4 * pl;
             __syncthreads();
             issue_upto(t);
-            if (RESTRICT)
-                accumulate(t);
         };
         for (int t = ia; t < ib; t += 2) {
             step(t, A, B);
             if (t + 1 < ib)
                 step(t + 1, B, A);
         }
+        if (RESTRICT)
+            accumulate(ib - 1, xoff ^ (4 * pl));
     } else {
         // =====================================================================
         // fused: colour c = SWEEP is relaxed on plane t+1, then the residual of
@@ -601,8 +605,10 @@ k_tile(const TileP P, const __grid_constant__ CUtensorMap tm_v,
             { double *tmp = nw; nw = nr; nr = tmp; }
             __syncthreads();
             issue_upto(t);
-            if (RESTRICT && do_res)
-                accumulate(t);
+            if (RESTRICT && do_res) {
+                accumulate(t, xoff);
+                xoff ^= 4 * pl;
+            }
         };
         for (int t = t0; t < ib; t += 2) {
             step(t, A, B);
@@ -702,9 +708,9 @@ bool shape_cfg(TileCfg &c, const Geo &gf, bool sweep, bool restr, const Geo *gc,
     return c.ok;
 }
 
-// Tile shape: as many rows per tile as possible (less halo, fewer redundant
-// rows) while the launch still has >= 6 blocks per SM to balance the load;
-// MGB_TILE_Q / MGB_TILE_R / MGB_TILE_MINCHUNK override (tuning).
+// Tile shape: the row count that balances a full last wave of blocks against
+// halo / recomputed rows; MGB_TILE_Q / MGB_TILE_R / MGB_TILE_MINCHUNK override
+// (tuning).
 TileCfg make_cfg(const Geo &gf, bool sweep, bool restr, const Geo *gc, int p_lo, int p_hi)
 {
     TileCfg c{};
@@ -715,17 +721,27 @@ TileCfg make_cfg(const Geo &gf, bool sweep, bool restr, const Geo *gc, int p_lo,
         shape_cfg(c, gf, sweep, restr, gc, p_lo, p_hi, qcap, r_env, minchunk);
         return c;
     }
-    static const int rows_restr[] = {7, 5, 4, 3, 2}, rows_norm[] = {7, 5, 4, 3};
+    // score = (how full the last wave of blocks is, 1 block per SM) x (share of a
+    // tile's rows that is not halo / recomputed)
+    static const int rows_restr[] = {7, 6, 5, 4, 3, 2}, rows_norm[] = {7, 6, 5, 4, 3};
     const int *cand = restr ? rows_restr : rows_norm;
-    const int ncand = restr ? 5 : 4;
+    const int ncand = restr ? 6 : 5;
     TileCfg best{};
+    double best_score = -1.;
     for (int i = 0; i < ncand; i++) {
         TileCfg t{};
         if (!shape_cfg(t, gf, sweep, restr, gc, p_lo, p_hi, qcap, cand[i], minchunk))
             continue;
-        best = t;
-        if ((long long)t.grid.x * t.grid.y * t.grid.z >= 6 * 148)
-            break;
+        const long long blocks = (long long)t.grid.x * t.grid.y * t.grid.z;
+        const long long rounds = (blocks + 147) / 148;
+        const double wave = (double)blocks / (double)(rounds * 148);
+        const double rows = restr ? (double)(2 * t.p.TY) / (2 * t.p.TY + 1 + (sweep ? 2 : 0))
+                                  : (double)t.p.TRo / (t.p.TRo + 2);
+        const double score = wave * rows;
+        if (score > best_score + 1e-9) {
+            best_score = score;
+            best = t;
+        }
     }
     return best;
 }

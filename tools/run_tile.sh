@@ -1,1 +1,2 @@
-for ch in 0 4 6 8 12 16 24 32 48 64; do echo "chunk=$ch"; for l in 8 9; do MGB_MARCH_CHUNK=$ch timeout 100 python tools/probe_tile.py --levels $l --reps 20 --which hs | awk '{print $1,$4,$5,$6,$7}'; done; done
+timeout 600 python -m pytest tests/test_gpu_operators.py -x -q -k "restrict or vcycle" 2>&1 | tail -2
+for l in 9 8 7; do timeout 100 python tools/probe_tile.py --levels $l --reps 10 --which rr,k1 | awk '{print $1,$2,$3,$4}'; done
