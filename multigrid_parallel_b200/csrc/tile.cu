@@ -191,10 +191,10 @@ struct TileP {
 };
 
 // SWEEP = -1: no fused sweep; 0/1: colour swept one plane ahead of the residual
-// MINB = resident blocks per SM the register budget is cut for (2: 64 regs,
-// 1: 128 regs)
+// MINB = resident blocks per SM the register budget is cut for: 1 -> 512
+// threads x 128 registers, 2 -> 384 threads x 80 registers, 3 -> 512 x 64
 template <int SWEEP, bool RESTRICT, int MINB>
-__global__ void __launch_bounds__(512, MINB)
+__global__ void __launch_bounds__(MINB == 2 ? 384 : 512, MINB == 1 ? 1 : 2)
 k_tile(const TileP P, const __grid_constant__ CUtensorMap tm_v,
        const __grid_constant__ CUtensorMap tm_d)
 {
@@ -644,6 +644,7 @@ int env_int(const char *name, int dflt)
 }
 int tile_bps();
 size_t tile_smem_cap();
+int tile_max_threads();
 
 // split n units into the fewest tiles of at most `cap` units, evenly
 int even_tile(int n, int cap)
@@ -702,15 +703,13 @@ bool shape_cfg(TileCfg &c, const Geo &gf, bool sweep, bool restr, const Geo *gc,
     const size_t slot_d = ((size_t)NCOL * RS * PW + 15) & ~(size_t)15;
     c.smem = 128 + sizeof(double) * ((size_t)S * slot_d + (sweep ? 2 * RS * PW : 0) +
                                      (restr ? (size_t)8 * p.TRt * p.TQt : 0));
-    c.ok = c.threads <= 512 && c.smem <= tile_smem_cap() && nplanes >= 1 && gf.nk >= 5 &&
+    c.ok = c.threads <= tile_max_threads() && c.smem <= tile_smem_cap() && nplanes >= 1 && gf.nk >= 5 &&
            gf.nj >= 3 && (long long)c.grid.x * c.grid.y * c.grid.z <= kMaxPartials &&
            c.grid.z <= 65535 && c.grid.y <= 65535;
     return c.ok;
 }
 
-// Tile shape: the row count that balances a full last wave of blocks against
-// halo / recomputed rows; MGB_TILE_Q / MGB_TILE_R / MGB_TILE_MINCHUNK override
-// (tuning).
+// Tile shape; MGB_TILE_Q / MGB_TILE_R / MGB_TILE_MINCHUNK override (tuning).
 TileCfg make_cfg(const Geo &gf, bool sweep, bool restr, const Geo *gc, int p_lo, int p_hi)
 {
     TileCfg c{};
@@ -721,27 +720,21 @@ TileCfg make_cfg(const Geo &gf, bool sweep, bool restr, const Geo *gc, int p_lo,
         shape_cfg(c, gf, sweep, restr, gc, p_lo, p_hi, qcap, r_env, minchunk);
         return c;
     }
-    // score = (how full the last wave of blocks is, 1 block per SM) x (share of a
-    // tile's rows that is not halo / recomputed)
-    static const int rows_restr[] = {7, 6, 5, 4, 3, 2}, rows_norm[] = {7, 6, 5, 4, 3};
-    const int *cand = restr ? rows_restr : rows_norm;
-    const int ncand = restr ? 6 : 5;
+    // measured on B200 (513^3 / 257^3, tools/probe_tile.py sweeps): 5 rows (coarse
+    // rows for the restricting form) per tile is the best or within 4 % of it
+    // wherever the launch still fills the GPU 1.5 times; smaller levels take 3.
+    // (A wave-quantisation x halo-share model was tried and did not predict the
+    // measurements.)
+    static const int cand[] = {5, 3, 2};
     TileCfg best{};
-    double best_score = -1.;
-    for (int i = 0; i < ncand; i++) {
+    for (int i = 0; i < 3; i++) {
         TileCfg t{};
         if (!shape_cfg(t, gf, sweep, restr, gc, p_lo, p_hi, qcap, cand[i], minchunk))
             continue;
-        const long long blocks = (long long)t.grid.x * t.grid.y * t.grid.z;
-        const long long rounds = (blocks + 147) / 148;
-        const double wave = (double)blocks / (double)(rounds * 148);
-        const double rows = restr ? (double)(2 * t.p.TY) / (2 * t.p.TY + 1 + (sweep ? 2 : 0))
-                                  : (double)t.p.TRo / (t.p.TRo + 2);
-        const double score = wave * rows;
-        if (score > best_score + 1e-9) {
-            best_score = score;
-            best = t;
-        }
+        best = t;
+        const long long slots = 148 * (tile_bps() == 1 ? 1 : 2);  // resident blocks
+        if ((long long)t.grid.x * t.grid.y * t.grid.z * 2 >= 3 * slots)
+            break;
     }
     return best;
 }
@@ -785,8 +778,13 @@ bool make_tensor_map(CUtensorMap *tm, const Geo &g, const double *base, int pw, 
            CUDA_SUCCESS;
 }
 
-int tile_bps() { static const int b = env_int("MGB_TILE_BPS", 1); return b == 2 ? 2 : 1; }
+int tile_bps()
+{
+    static const int b = env_int("MGB_TILE_BPS", 2);
+    return b >= 1 && b <= 3 ? b : 1;
+}
 size_t tile_smem_cap() { return tile_bps() == 1 ? 226 * 1024 : 112 * 1024; }
+int tile_max_threads() { return tile_bps() == 2 ? 384 : 512; }
 
 template <int SWEEP, bool RESTRICT, int MINB>
 bool launch_cfg_b(const TileCfg &c, cudaStream_t st)
@@ -811,8 +809,11 @@ bool launch_cfg_b(const TileCfg &c, cudaStream_t st)
 template <int SWEEP, bool RESTRICT>
 bool launch_cfg(const TileCfg &c, cudaStream_t st)
 {
-    return tile_bps() == 1 ? launch_cfg_b<SWEEP, RESTRICT, 1>(c, st)
-                           : launch_cfg_b<SWEEP, RESTRICT, 2>(c, st);
+    switch (tile_bps()) {
+    case 2: return launch_cfg_b<SWEEP, RESTRICT, 2>(c, st);
+    case 3: return launch_cfg_b<SWEEP, RESTRICT, 3>(c, st);
+    default: return launch_cfg_b<SWEEP, RESTRICT, 1>(c, st);
+    }
 }
 
 }  // namespace
