@@ -48,6 +48,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
+#include <type_traits>
 
 #include "kernels.h"
 
@@ -354,27 +355,33 @@ k_tile(const TileP P, const __grid_constant__ CUtensorMap tm_v,
     // phase B of a RESTRICT step: the coarse threads add plane t's nine products
     // to their open sum; an odd plane closes coarse plane I and opens I+1 with
     // the same products (mg_3d.h:980-989, ti-major order)
-    auto accumulate = [&](int t, int xo) {
+    // the three residual columns a coarse point reads (buffer 0, first of its rows)
+    const double *pxa = ccol ? xr + pl : xr + 3 * pl - 1;
+    const double *pxm = ccol ? xr + 2 * pl : xr;
+    const double *pxc = ccol ? xr + 3 * pl : xr + pl;
+    // ODD = parity of the global fine plane t, known at compile time where the
+    // step loop is unrolled by two (a chunk of the restricting form always starts
+    // on an odd plane)
+    auto accumulate_p = [&](int t, int xo, auto odd_tag) {
+        constexpr bool ODD = decltype(odd_tag)::value;
         if (cthr) {
-            const int ig = g.i0 + t;
-            const bool odd = ig & 1;
-            const double wf = odd ? 0.5 : 1.0;  // ti = 0/2 vs ti = 1
-            const double *x = xr + xo;
+            constexpr double wf = ODD ? 0.5 : 1.0;  // ti = 0/2 vs ti = 1
             double a = cacc, sfresh = 0.;
 #pragma unroll
-            for (int tj = 0; tj < 3; tj++, x += TQt) {
-                double xa, xm, xc;
-                if (ccol) { xa = x[pl]; xm = x[2 * pl]; xc = x[3 * pl]; }
-                else      { xa = x[3 * pl - 1]; xm = x[0]; xc = x[pl]; }
+            for (int tj = 0; tj < 3; tj++) {
+                const double xa = pxa[xo + tj * TQt], xm = pxm[xo + tj * TQt],
+                             xc = pxc[xo + tj * TQt];
                 const double wc = (tj == 1 ? 0.125 : 0.0625) * wf;  // tk = 1
                 const double we = 0.5 * wc;                          // tk = 0, 2
                 const double q0 = __dmul_rn(xa, we), q1 = __dmul_rn(xm, wc),
                              q2 = __dmul_rn(xc, we);
                 a = __dadd_rn(__dadd_rn(__dadd_rn(a, q0), q1), q2);
-                sfresh = __dadd_rn(__dadd_rn(__dadd_rn(sfresh, q0), q1), q2);
+                if (ODD)
+                    sfresh = __dadd_rn(__dadd_rn(__dadd_rn(sfresh, q0), q1), q2);
             }
-            if (odd) {
+            if (ODD) {
                 if (have_cur) {  // plane 2I+1 closes coarse plane I
+                    const int ig = g.i0 + t;
                     const int Il = ((ig - 1) >> 1) - P.gc.i0;
                     const int cc = (P.gc.i0 + Il + cJ + cK) & 1;
                     P.dc[(long long)cc * P.gc.cs + ((long long)Il * P.gc.nj + cJ) * P.gc.kh +
@@ -386,6 +393,14 @@ k_tile(const TileP P, const __grid_constant__ CUtensorMap tm_v,
                 cacc = a;
             }
         }
+    };
+    using OddT = std::true_type;
+    using EvenT = std::false_type;
+    auto accumulate = [&](int t, int xo) {
+        if ((g.i0 + t) & 1)
+            accumulate_p(t, xo, OddT{});
+        else
+            accumulate_p(t, xo, EvenT{});
     };
     auto put_residuals = [&](double n0, double n1, double n2, double n3, bool counted) {
         if (RESTRICT) {
@@ -437,7 +452,7 @@ k_tile(const TileP P, const __grid_constant__ CUtensorMap tm_v,
             A.dO = ld2(pd + (g.cs - dE_off));
         }
         const bool mE0 = fk & 1, mE1 = fk & 2, mO0 = fk & 4, mO1 = fk & 8;
-        auto step = [&](int t, const Pre &cur, Pre &nxt) {
+        auto step = [&](int t, const Pre &cur, Pre &nxt, auto prev_parity) {
             wait_next();  // plane t+1
             const double *q_nxt = ring + n_s * slot_d + so;
             double n0 = 0., n1 = 0., n2 = 0., n3 = 0.;
@@ -472,7 +487,7 @@ k_tile(const TileP P, const __grid_constant__ CUtensorMap tm_v,
             // residuals of plane t (other buffer): its dependent add chain overlaps
             // with independent work instead of standing alone behind a barrier
             if (RESTRICT && t > ia)
-                accumulate(t - 1, xoff ^ (4 * pl));
+                accumulate_p(t - 1, xoff ^ (4 * pl), prev_parity);
             q_cur = q_nxt;
             n_s = n_s + 1 == S ? 0 : n_s + 1;
             offE = offO; offO = col1 - offE;
@@ -481,13 +496,20 @@ k_tile(const TileP P, const __grid_constant__ CUtensorMap tm_v,
             __syncthreads();
             issue_upto(t);
         };
-        for (int t = ia; t < ib; t += 2) {
-            step(t, A, B);
-            if (t + 1 < ib)
-                step(t + 1, B, A);
-        }
-        if (RESTRICT)
+        if (RESTRICT) {  // chunks start on an odd global plane: t - 1 is even in the first step
+            for (int t = ia; t < ib; t += 2) {
+                step(t, A, B, EvenT{});
+                if (t + 1 < ib)
+                    step(t + 1, B, A, OddT{});
+            }
             accumulate(ib - 1, xoff ^ (4 * pl));
+        } else {
+            for (int t = ia; t < ib; t += 2) {
+                step(t, A, B, EvenT{});
+                if (t + 1 < ib)
+                    step(t + 1, B, A, OddT{});
+            }
+        }
     } else {
         // =====================================================================
         // fused: colour c = SWEEP is relaxed on plane t+1, then the residual of
