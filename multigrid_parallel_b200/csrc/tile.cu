@@ -194,7 +194,10 @@ struct TileP {
 // SWEEP = -1: no fused sweep; 0/1: colour swept one plane ahead of the residual
 // MINB = resident blocks per SM the register budget is cut for: 1 -> 512
 // threads x 128 registers, 2 -> 384 threads x 80 registers, 3 -> 512 x 64
-template <int SWEEP, bool RESTRICT, int MINB>
+// TRT x TQT = thread tile fixed at compile time (0: taken from P at run time):
+// the step loop is issue-bound, and with constant tile extents the shared-memory
+// address arithmetic folds into immediates
+template <int SWEEP, bool RESTRICT, int MINB, int TRT = 0, int TQT = 0>
 __global__ void __launch_bounds__(MINB == 2 ? 384 : 512, MINB == 1 ? 1 : 2)
 k_tile(const TileP P, const __grid_constant__ CUtensorMap tm_v,
        const __grid_constant__ CUtensorMap tm_d)
@@ -207,7 +210,7 @@ k_tile(const TileP P, const __grid_constant__ CUtensorMap tm_v,
 
     extern __shared__ __align__(128) unsigned char tile_smem[];
     const Geo &g = P.gf;
-    const int TRt = P.TRt, TQt = P.TQt;
+    const int TRt = TRT > 0 ? TRT : P.TRt, TQt = TQT > 0 ? TQT : P.TQt;
     const int RS = TRt + 2;        // slot rows: thread rows + one halo row each side
     const int PW = 2 * (TQt + 2);  // slot row pitch in doubles: pairs -1 .. TQt
     const int slot_d = (NCOL * RS * PW + 15) & ~15;  // slots start on 128-byte boundaries (TMA)
@@ -808,12 +811,12 @@ int tile_bps()
 size_t tile_smem_cap() { return tile_bps() == 1 ? 226 * 1024 : 112 * 1024; }
 int tile_max_threads() { return tile_bps() == 2 ? 384 : 512; }
 
-template <int SWEEP, bool RESTRICT, int MINB>
+template <int SWEEP, bool RESTRICT, int MINB, int TRT = 0, int TQT = 0>
 bool launch_cfg_b(const TileCfg &c, cudaStream_t st)
 {
     static bool attr = false;
     if (!attr) {
-        cudaFuncSetAttribute(k_tile<SWEEP, RESTRICT, MINB>,
+        cudaFuncSetAttribute(k_tile<SWEEP, RESTRICT, MINB, TRT, TQT>,
                              cudaFuncAttributeMaxDynamicSharedMemorySize,
                              MINB == 1 ? 226 * 1024 : 112 * 1024);
         attr = true;
@@ -823,7 +826,7 @@ bool launch_cfg_b(const TileCfg &c, cudaStream_t st)
     if (!make_tensor_map(&tm_v, c.p.gf, c.p.v, pw, rs, SWEEP >= 0 ? 1 : 2) ||
         !make_tensor_map(&tm_d, c.p.gf, c.p.d, pw, rs, 2))
         return false;
-    k_tile<SWEEP, RESTRICT, MINB><<<c.grid, c.threads, c.smem, st>>>(c.p, tm_v, tm_d);
+    k_tile<SWEEP, RESTRICT, MINB, TRT, TQT><<<c.grid, c.threads, c.smem, st>>>(c.p, tm_v, tm_d);
     ++*launch_counter();
     return true;
 }
@@ -831,6 +834,15 @@ bool launch_cfg_b(const TileCfg &c, cudaStream_t st)
 template <int SWEEP, bool RESTRICT>
 bool launch_cfg(const TileCfg &c, cudaStream_t st)
 {
+    // the shapes the big levels of 2^k+1 cubes get (513^3, 1025^3, ...): compiled
+    // with constant tile extents
+    static const int fixed = env_int("MGB_TILE_FIXED", 1);
+    if (fixed && SWEEP < 0 && tile_bps() == 2) {
+        if (RESTRICT && c.p.TRt == 11 && c.p.TQt == 34)
+            return launch_cfg_b<-1, RESTRICT, 2, RESTRICT ? 11 : 5, RESTRICT ? 34 : 43>(c, st);
+        if (!RESTRICT && c.p.TRt == 5 && c.p.TQt == 43)
+            return launch_cfg_b<-1, RESTRICT, 2, RESTRICT ? 11 : 5, RESTRICT ? 34 : 43>(c, st);
+    }
     switch (tile_bps()) {
     case 2: return launch_cfg_b<SWEEP, RESTRICT, 2>(c, st);
     case 3: return launch_cfg_b<SWEEP, RESTRICT, 3>(c, st);
