@@ -34,9 +34,10 @@ METRIC = "vcycle_dof_per_s"
 UNIT = "DOF*cycles/s"
 HALF_SWEEP_BYTES_PER_DOF = 12.0       # read 1/2 v, read 1/2 d, write 1/2 v
 # SURVEY 8(d) algorithmic bytes per DOF of the other finest-level stages
-STAGE_BYTES_PER_DOF = {"CalcResidual1": ("k_tile<-1,restrict> (residual+restrict)", 17.0),
-                       "Prolongate&Correct": ("k_prolong_correct8", 17.0),
-                       "CalcResidual2": ("k_tile<-1,norm> (residual norm)", 16.0)}
+# stage -> (kernel as named in profiles/traffic.json, what it is, bytes per DOF)
+STAGE_BYTES_PER_DOF = {"CalcResidual1": ("k_tile<-1,1,2,11,34>", "residual+restrict (TMA tile kernel)", 17.0),
+                       "Prolongate&Correct": ("k_prolong_correct8", "prolongation+correction", 17.0),
+                       "CalcResidual2": ("k_tile<-1,0,2,5,43>", "residual norm (TMA tile kernel)", 16.0)}
 
 
 def ncu_traffic(kernel):
@@ -240,10 +241,10 @@ def run_ours(args):
     for st in range(7):
         name = m.STAGE_NAMES[st]
         if name in STAGE_BYTES_PER_DOF and stage[st] > 0:
-            kern, bpd = STAGE_BYTES_PER_DOF[name]
+            kern, what, bpd = STAGE_BYTES_PER_DOF[name]
             gbs = bpd * dof / stage[st] / 1e9
-            others[kern] = {"achieved": gbs, "frac": gbs / peak, "bytes_per_dof": bpd,
-                            "launch_us": stage[st] * 1e6}
+            others[kern] = {"what": what, "achieved": gbs, "frac": gbs / peak, "bytes_per_dof": bpd,
+                            "launch_us": stage[st] * 1e6, "traffic": ncu_traffic(kern)}
 
     # end to end through the C ABI with host buffers (pinned), whole solve
     import torch
@@ -294,8 +295,8 @@ def run_ours(args):
                 "d2h_bytes_per_step": int(dof * 8), "seconds_per_solve": t_e2e, "cycles": cycles,
                 "step": "one full solve: upload grid+rhs from pinned host memory, V-cycles to "
                         "1e-8*||d||, download grid"},
-        "roofline": {"bound": "hbm", "kernel": "k_half_sweep", "achieved": achieved, "peak": peak,
-                     "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic("k_half_sweep"),
+        "roofline": {"bound": "hbm", "kernel": "k_half_sweep_pipe", "achieved": achieved, "peak": peak,
+                     "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic("k_half_sweep_pipe"),
                      "peak_source": peak_src, "bytes_per_dof": HALF_SWEEP_BYTES_PER_DOF,
                      "avg_launch_us": t_half * 1e6, "share_of_finest_level": share,
                      "frac_of_8TBs_nominal": achieved / 8000.0,
