@@ -385,6 +385,8 @@ void launch_half_sweep(const Geo &g, double *v, const double *d, double hSq,
 {
     if (il_hi <= il_lo)
         return;
+    if (launch_tile_half_sweep(g, v, d, hSq, colour, il_lo, il_hi, st))
+        return;
     static const int pipe = getenv("MGB_SWEEP_PIPE") ? atoi(getenv("MGB_SWEEP_PIPE")) : 1;
     if (pipe) {
         static const int occp = resident_blocks(k_half_sweep_pipe<1>, 256, 0);

@@ -103,6 +103,10 @@ struct TailP {
 };
 void launch_coarse_tail(const TailP &p, cudaStream_t st);
 
+// the half-sweep through the TMA ring (tile.cu); false: level too small, use the marching kernel
+bool launch_tile_half_sweep(const Geo &g, double *v, const double *d, double hSq, int colour,
+                            int il_lo, int il_hi, cudaStream_t st);
+
 // dense coarse operator + LU (mg_3d.h:147-273, gauss_elim.h:9-60)
 void launch_coarse_matrix(double *A, int ni, int nj, int nk, double h,
                           cudaStream_t st);

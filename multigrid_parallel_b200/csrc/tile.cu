@@ -650,6 +650,135 @@ k_tile(const TileP P, const __grid_constant__ CUtensorMap tm_v,
 }
 
 // ---------------------------------------------------------------------------
+// The half-sweep itself on the same machinery (mg_3d.h:432-443, 658-702): the
+// other colour arrives through the TMA ring (own pair of planes t-1, t+1 kept in
+// registers / read from the next slot, rows j+-1 and the k neighbour read from
+// the slot of plane t), the rhs box is prefetched into L2 by TMA and read one
+// step ahead, the new pair goes straight to HBM.  No exchange between threads:
+// the barrier per plane only recycles ring slots.
+// ---------------------------------------------------------------------------
+template <int COLOUR, int TRT, int TQT>
+__global__ void __launch_bounds__(384, 2)
+k_tile_sweep(const TileP P, const __grid_constant__ CUtensorMap tm_v,
+             const __grid_constant__ CUtensorMap tm_d)
+{
+    constexpr int S = 4;
+    extern __shared__ __align__(128) unsigned char tile_smem[];
+    const Geo &g = P.gf;
+    const int TRt = TRT > 0 ? TRT : P.TRt, TQt = TQT > 0 ? TQT : P.TQt;
+    const int RS = TRt + 2, PW = 2 * (TQt + 2);
+    const int slot_d = (RS * PW + 15) & ~15;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(tile_smem);
+    double *ring = reinterpret_cast<double *>(tile_smem + 128);
+    const int tid = threadIdx.x;
+    const int jl = tid / TQt, ml = tid - jl * TQt;
+    const bool live = jl < TRt;
+    const int npair = g.kh >> 1;
+    const int jt0 = blockIdx.y * P.TRo, mq0 = blockIdx.x * P.TQo;
+    const int j = jt0 + jl, mq = mq0 + ml;
+    const bool calc = live && j >= 1 && j <= g.nj - 2 && mq >= 0 && mq < npair;
+    const int kmax = g.nk - 2;
+    const int ia = P.p_lo + blockIdx.z * P.chunk;
+    const int ib = min(ia + P.chunk, P.p_hi);
+    if (ia >= ib)
+        return;
+    const int pr0 = ia - 1, plast = ib;
+    const uint32_t ring_u32 = smem_u32(ring), bars_u32 = smem_u32(bars);
+    const uint32_t box_bytes = (uint32_t)(RS * PW) * 8u, slot_bytes = (uint32_t)slot_d * 8u;
+    const int c0 = 2 * (mq0 - 1), c1 = jt0 - 1;
+    if (tid == 0) {
+        for (int s = 0; s < S; s++)
+            mbar_init(bars_u32 + 8 * s, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    int iss_p = pr0, iss_s = 0;
+    auto issue_upto = [&](int dead) {
+        if (tid != 0)
+            return;
+        while (iss_p <= plast && iss_p - S <= dead) {
+            const uint32_t bar = bars_u32 + 8 * iss_s;
+            mbar_arrive_expect_tx(bar, box_bytes);
+            tma_load_4d(ring_u32 + iss_s * slot_bytes, &tm_v, c0, c1, iss_p, COLOUR ^ 1, bar);
+            if (iss_p >= ia && iss_p < ib)
+                tma_prefetch_4d(&tm_d, c0, c1, iss_p, COLOUR);
+            iss_p++;
+            iss_s = iss_s + 1 == S ? 0 : iss_s + 1;
+        }
+    };
+    int w_s = 0;
+    uint32_t w_par = 0;
+    auto wait_next = [&]() {
+        mbar_wait(bars_u32 + 8 * w_s, w_par);
+        if (++w_s == S) {
+            w_s = 0;
+            w_par ^= 1;
+        }
+    };
+    issue_upto(pr0 - 1);
+
+    const long long offq = (long long)j * g.kh + 2 * mq;
+    const int so = (jl + 1) * PW + 2 * (ml + 1);
+    const double sixth = 1. / 6, hSq = P.hSq;
+    const int fk = ((mq >= 1 && 4 * mq <= kmax) ? 1 : 0) | ((4 * mq + 2 <= kmax) ? 2 : 0) |
+                   ((4 * mq + 1 <= kmax) ? 4 : 0) | ((4 * mq + 3 <= kmax) ? 8 : 0);
+    const double2 z2 = make_double2(0., 0.);
+    wait_next();  // plane ia-1
+    wait_next();  // plane ia
+    double2 bot = z2, mid = z2;
+    const double *q_cur = ring + slot_d + so;
+    int n_s = 2;
+    if (live) {
+        bot = ld2(ring + so);
+        mid = ld2(q_cur);
+    }
+    const double *pd = P.d + (long long)COLOUR * g.cs + (long long)ia * g.pj + offq;
+    double *pc = P.vw + (long long)COLOUR * g.cs + (long long)ia * g.pj + offq;
+    double2 A = z2, B = z2;
+    if (calc)
+        A = ld2(pd);
+    int kp = (COLOUR ^ (g.i0 + ia + j)) & 1;
+    auto step = [&](int t, const double2 &cur, double2 &nxt) {
+        wait_next();  // plane t+1
+        const double *q_nxt = ring + n_s * slot_d + so;
+        pd += g.pj;
+        if (live) {
+            const double2 top = ld2(q_nxt);
+            if (calc) {
+                if (t + 1 < ib)
+                    nxt = ld2(pd);
+                const double2 jm = ld2(q_cur - PW), jp = ld2(q_cur + PW);
+                double a0, a1, a2;
+                if (kp) { a0 = mid.x; a1 = mid.y; a2 = q_cur[2]; }
+                else    { a0 = q_cur[-1]; a1 = mid.x; a2 = mid.y; }
+                const double r0 = gs_point(bot.x, top.x, jm.x, jp.x, a0, a1, hSq, cur.x, sixth);
+                const double r1 = gs_point(bot.y, top.y, jm.y, jp.y, a1, a2, hSq, cur.y, sixth);
+                const int mk = fk >> (2 * kp);
+                if ((mk & 3) == 3)
+                    st2(pc, r0, r1);
+                else if (mk & 1)
+                    pc[0] = r0;
+                else if (mk & 2)
+                    pc[1] = r1;
+            }
+            bot = mid;
+            mid = top;
+        }
+        q_cur = q_nxt;
+        n_s = n_s + 1 == S ? 0 : n_s + 1;
+        pc += g.pj;
+        kp ^= 1;
+        __syncthreads();
+        issue_upto(t);
+    };
+    for (int t = ia; t < ib; t += 2) {
+        step(t, A, B);
+        if (t + 1 < ib)
+            step(t + 1, B, A);
+    }
+}
+
+// ---------------------------------------------------------------------------
 // host side: tile shapes and launches
 // ---------------------------------------------------------------------------
 namespace {
@@ -904,6 +1033,69 @@ bool launch_tile_residual_restrict(const Geo &gf, double *vf, const double *df, 
     c.p.partials = nullptr; c.p.dc = dc;
     return colour < 0 ? launch_cfg<-1, true>(c, st)
                       : (colour == 0 ? launch_cfg<0, true>(c, st) : launch_cfg<1, true>(c, st));
+}
+
+// one colour of the smoother over local planes [il_lo, il_hi) through the TMA ring
+bool launch_tile_half_sweep(const Geo &g, double *v, const double *d, double hSq, int colour,
+                            int il_lo, int il_hi, cudaStream_t st)
+{
+    // measured (B200): 513^3 249 us vs 275 us for the L1-based marching kernel
+    // (6.5 TB/s = 99 % of the measured copy peak), 1025^3 2.21 vs 2.24 ms, but
+    // 257^3 43.6 vs 41.4 us: planes of >= 200k points only
+    static const int on = env_int("MGB_TILE_SWEEP", 1);
+    static const long long min_plane = env_int("MGB_TILE_SWEEP_MIN_PLANE", 200000);
+    if (!on || !tile_enabled() || il_hi - il_lo < 8 || !tile_worthwhile(g) ||
+        ((long long)g.nj * g.nk < min_plane && g_tile_min_plane > 0))
+        return false;
+    TileCfg c{};
+    const int rows = env_int("MGB_TILE_SWEEP_R", 6), qcap = env_int("MGB_TILE_SWEEP_Q", 43);
+    TileP &p = c.p;
+    p.gf = g;
+    const int nq = (g.nk + 3) / 4;
+    p.TQo = p.TQt = even_tile(nq, qcap);
+    p.TRo = p.TRt = even_tile(g.nj, rows);
+    c.grid.x = (nq + p.TQo - 1) / p.TQo;
+    c.grid.y = (g.nj + p.TRo - 1) / p.TRo;
+    const int nplanes = il_hi - il_lo;
+    const long long per_layer = (long long)c.grid.x * c.grid.y;
+    int want = (int)((16LL * 148 + per_layer - 1) / per_layer);
+    int maxch = nplanes / env_int("MGB_TILE_MINCHUNK", 24);
+    if (maxch < 1) maxch = 1;
+    if (want > maxch) want = maxch;
+    if (want < 1) want = 1;
+    p.chunk = (nplanes + want - 1) / want;
+    c.grid.z = (nplanes + p.chunk - 1) / p.chunk;
+    p.p_lo = il_lo;
+    p.p_hi = il_hi;
+    c.threads = ((p.TRt * p.TQt + 31) / 32) * 32;
+    const size_t RS = p.TRt + 2, PW = 2 * (p.TQt + 2);
+    const size_t slot_d = (RS * PW + 15) & ~(size_t)15;
+    c.smem = 128 + 4 * slot_d * 8;
+    if (c.threads > 384 || c.smem > 112 * 1024 || c.grid.z > 65535 || c.grid.y > 65535)
+        return false;
+    p.v = v; p.vw = v; p.d = d; p.hSq = hSq; p.invHsq = 0.;
+    CUtensorMap tm_v, tm_d;
+    if (!make_tensor_map(&tm_v, g, v, (int)PW, (int)RS, 1) ||
+        !make_tensor_map(&tm_d, g, d, (int)PW, (int)RS, 1))
+        return false;
+    static bool attr = false;
+    if (!attr) {
+        cudaFuncSetAttribute(k_tile_sweep<0, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024);
+        cudaFuncSetAttribute(k_tile_sweep<1, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024);
+        cudaFuncSetAttribute(k_tile_sweep<0, 6, 43>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024);
+        cudaFuncSetAttribute(k_tile_sweep<1, 6, 43>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024);
+        attr = true;
+    }
+    const bool fixed = p.TRt == 6 && p.TQt == 43;
+    if (colour) {
+        if (fixed) k_tile_sweep<1, 6, 43><<<c.grid, c.threads, c.smem, st>>>(c.p, tm_v, tm_d);
+        else k_tile_sweep<1, 0, 0><<<c.grid, c.threads, c.smem, st>>>(c.p, tm_v, tm_d);
+    } else {
+        if (fixed) k_tile_sweep<0, 6, 43><<<c.grid, c.threads, c.smem, st>>>(c.p, tm_v, tm_d);
+        else k_tile_sweep<0, 0, 0><<<c.grid, c.threads, c.smem, st>>>(c.p, tm_v, tm_d);
+    }
+    ++*launch_counter();
+    return true;
 }
 
 }  // namespace mgb

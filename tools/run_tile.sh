@@ -1,5 +1,4 @@
-set -x
-python bench.py > gpurun_out/bench_r01d.log 2>&1; tail -1 gpurun_out/bench_r01d.log | cut -c1-400
-python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref_r01d.log 2>&1; tail -1 gpurun_out/bench_ref_r01d.log | cut -c1-200
-python tools/probe_tile.py --levels 9 --reps 2 --which hs,pc,norm,rr > gpurun_out/pt_plain3.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:"k_half_sweep_pipe|k_tile|k_prolong_correct8" -c 12 -o gpurun_out/prof_r01d python tools/probe_tile.py --levels 9 --reps 2 --which hs,pc,norm,rr > gpurun_out/ncu_r01d.log 2>&1
-python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/bench_short_plain.log 2>&1 && ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches_r01d.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_launches.log 2>&1
+timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -2
+timeout 100 python tools/probe.py --levels 9 --reps 5 --cycles 20 2>&1 | grep -E "vcycle|half"
+python tools/bench_rbgs.py --n 513 --iters 30 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('rbgs513', d['us_per_full_sweep'], d['rbgs_gbs'], d['frac_of_measured_peak'], d['frac_of_8TBs_nominal'])"
+python bench.py --no-cpu-baseline | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print('bench', d['ms_per_step'], d['value'], d['roofline']['frac'], d['roofline']['avg_launch_us'], d['e2e']['seconds_per_solve'])"
