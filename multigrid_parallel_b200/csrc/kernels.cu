@@ -998,6 +998,8 @@ void launch_prolong_correct(const Geo &gc, const double *ec, const Geo &gf,
 {
     if (il_hi <= il_lo)
         return;
+    if (launch_tile_prolong(gc, ec, gf, ef, il_lo, il_hi, st))
+        return;
     static const int wide = getenv("MGB_PROLONG_WIDE") ? atoi(getenv("MGB_PROLONG_WIDE")) : 1;
     if (wide) {
         static const int occ8 = resident_blocks(k_prolong_correct8, 256, 0);

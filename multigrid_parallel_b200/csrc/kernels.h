@@ -107,6 +107,11 @@ void launch_coarse_tail(const TailP &p, cudaStream_t st);
 bool launch_tile_half_sweep(const Geo &g, double *v, const double *d, double hSq, int colour,
                             int il_lo, int il_hi, cudaStream_t st);
 
+// prolongation + correction through the TMA ring (tile.cu); false: use launch_prolong_correct's
+// marching kernels
+bool launch_tile_prolong(const Geo &gc, const double *ec, const Geo &gf, double *ef, int il_lo,
+                         int il_hi, cudaStream_t st);
+
 // dense coarse operator + LU (mg_3d.h:147-273, gauss_elim.h:9-60)
 void launch_coarse_matrix(double *A, int ni, int nj, int nk, double h,
                           cudaStream_t st);

@@ -779,6 +779,186 @@ k_tile_sweep(const TileP P, const __grid_constant__ CUtensorMap tm_v,
 }
 
 // ---------------------------------------------------------------------------
+// Prolongation + correction (mg_3d.h:1000-1145) on the same machinery: the fine
+// planes (both colours) stream through the TMA ring three planes ahead, the
+// corrected values go straight back to HBM; the coarse rows come through L1
+// (coarse plane I+1 is requested during the even fine plane, used on the odd
+// one and becomes plane I of the next pair).  Chunks start on even fine planes.
+// ---------------------------------------------------------------------------
+struct TC3 {
+    double x, y, z;  // coarse entries K = 2q, 2q+1, 2q+2
+};
+__device__ __forceinline__ TC3 t_ld_c3(const Geo &gc, const double *__restrict__ ec, int Il, int J,
+                                       int q)
+{
+    const int S = (gc.i0 + Il + J) & 1;  // colour of the even K in this coarse row
+    const long long row = ((long long)Il * gc.nj + J) * gc.kh;
+    const double *e0 = ec + (long long)S * gc.cs + row;
+    const double *e1 = ec + (long long)(S ^ 1) * gc.cs + row;
+    TC3 r;
+    r.x = e0[q];
+    r.y = e1[q];
+    r.z = e0[q + 1];
+    return r;
+}
+__device__ __forceinline__ double t_add0(double x) { return __dadd_rn(0., x); }
+// fine point with even k on a coarse column (corner orders of mg_3d.h:1080-1138)
+__device__ __forceinline__ double t_pc_even(int oi, int oj, double a0, double a1, double b0,
+                                            double b1)
+{
+    if (!oi && !oj)
+        return a0;
+    if (oi && !oj)
+        return __dmul_rn(__dadd_rn(t_add0(a0), b0), 0.5);
+    if (!oi)
+        return __dmul_rn(__dadd_rn(t_add0(a0), a1), 0.5);
+    double t = __dadd_rn(t_add0(a0), a1);
+    t = __dadd_rn(t, b0);
+    t = __dadd_rn(t, b1);
+    return __dmul_rn(t, 0.25);
+}
+// fine point with odd k between two coarse columns (mg_3d.h:1023-1079, 1119-1125)
+__device__ __forceinline__ double t_pc_odd(int oi, int oj, double a0x, double a0y, double a1x,
+                                           double a1y, double b0x, double b0y, double b1x,
+                                           double b1y)
+{
+    if (!oi && !oj)
+        return __dmul_rn(__dadd_rn(t_add0(a0x), a0y), 0.5);
+    if (oi && !oj) {
+        double t = __dadd_rn(t_add0(a0x), b0x);
+        t = __dadd_rn(t, a0y);
+        t = __dadd_rn(t, b0y);
+        return __dmul_rn(t, 0.25);
+    }
+    if (!oi) {
+        double t = __dadd_rn(t_add0(a0x), a1x);
+        t = __dadd_rn(t, a0y);
+        t = __dadd_rn(t, a1y);
+        return __dmul_rn(t, 0.25);
+    }
+    double t = __dadd_rn(t_add0(a0x), a0y);
+    t = __dadd_rn(t, a1x);
+    t = __dadd_rn(t, a1y);
+    t = __dadd_rn(t, b0x);
+    t = __dadd_rn(t, b0y);
+    t = __dadd_rn(t, b1x);
+    t = __dadd_rn(t, b1y);
+    return __dmul_rn(t, 0.125);
+}
+
+template <int TRT, int TQT>
+__global__ void __launch_bounds__(384, 2)
+k_tile_prolong(const TileP P, const double *__restrict__ ec,
+               const __grid_constant__ CUtensorMap tm_v)
+{
+    constexpr int S = 4;
+    extern __shared__ __align__(128) unsigned char tile_smem[];
+    const Geo &g = P.gf, &gc = P.gc;
+    const int TRt = TRT > 0 ? TRT : P.TRt, TQt = TQT > 0 ? TQT : P.TQt;
+    const int RS = TRt + 2, PW = 2 * (TQt + 2);
+    const int slot_d = (2 * RS * PW + 15) & ~15;
+    const int col1 = RS * PW;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(tile_smem);
+    double *ring = reinterpret_cast<double *>(tile_smem + 128);
+    const int tid = threadIdx.x;
+    const int jl = tid / TQt, ml = tid - jl * TQt;
+    const int npair = g.kh >> 1;
+    const int jt0 = blockIdx.y * P.TRo, mq0 = blockIdx.x * P.TQo;
+    const int j = jt0 + jl, mq = mq0 + ml;
+    const int k0 = 4 * mq;
+    const bool work = jl < TRt && j < g.nj && mq < npair && k0 < g.nk;
+    const bool v1 = k0 + 1 < g.nk, v2 = k0 + 2 < g.nk, v3 = k0 + 3 < g.nk;
+    const int ia = P.p_lo + blockIdx.z * P.chunk;  // even global plane
+    const int ib = min(ia + P.chunk, P.p_hi);
+    if (ia >= ib)
+        return;
+    const int pr0 = ia, plast = ib - 1;
+    const uint32_t ring_u32 = smem_u32(ring), bars_u32 = smem_u32(bars);
+    const uint32_t box_bytes = (uint32_t)(2 * RS * PW) * 8u, slot_bytes = (uint32_t)slot_d * 8u;
+    const int c0 = 2 * (mq0 - 1), c1 = jt0 - 1;
+    if (tid == 0) {
+        for (int s = 0; s < S; s++)
+            mbar_init(bars_u32 + 8 * s, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    int iss_p = pr0, iss_s = 0;
+    auto issue_upto = [&](int dead) {
+        if (tid != 0)
+            return;
+        while (iss_p <= plast && iss_p - S <= dead) {
+            const uint32_t bar = bars_u32 + 8 * iss_s;
+            mbar_arrive_expect_tx(bar, box_bytes);
+            tma_load_4d(ring_u32 + iss_s * slot_bytes, &tm_v, c0, c1, iss_p, 0, bar);
+            iss_p++;
+            iss_s = iss_s + 1 == S ? 0 : iss_s + 1;
+        }
+    };
+    int w_s = 0;
+    uint32_t w_par = 0;
+    auto wait_next = [&]() {
+        mbar_wait(bars_u32 + 8 * w_s, w_par);
+        if (++w_s == S) {
+            w_s = 0;
+            w_par ^= 1;
+        }
+    };
+    issue_upto(pr0 - 1);
+
+    const long long offq = (long long)j * g.kh + 2 * mq;
+    const int so = (jl + 1) * PW + 2 * (ml + 1);
+    const int oj = j & 1, J0 = j >> 1;
+    int I = ((g.i0 + ia) >> 1) - gc.i0;  // coarse plane under fine plane ia
+    TC3 A0{0., 0., 0.}, A1 = A0, B0 = A0, B1 = A0;
+    if (work) {
+        A0 = t_ld_c3(gc, ec, I, J0, mq);
+        A1 = oj ? t_ld_c3(gc, ec, I, J0 + 1, mq) : A0;
+    }
+    int c_s = 0;  // slot of plane t
+    double *pf = P.vw + (long long)ia * g.pj + offq;  // colour 0, plane t
+    // one fine plane: add the interpolated correction to the four points of the quad
+    auto plane = [&](int t, int oi) {
+        wait_next();  // plane t
+        const double *q = ring + c_s * slot_d + so;
+        if (work) {
+            const int s = (g.i0 + t + j) & 1;  // colour holding the even k of this row
+            const double2 fe = ld2(q + (s ? col1 : 0)), fo = ld2(q + (s ? 0 : col1));
+            const double e0 = t_pc_even(oi, oj, A0.x, A1.x, B0.x, B1.x);
+            const double e1 = t_pc_even(oi, oj, A0.y, A1.y, B0.y, B1.y);
+            const double o0 = t_pc_odd(oi, oj, A0.x, A0.y, A1.x, A1.y, B0.x, B0.y, B1.x, B1.y);
+            const double o1 = t_pc_odd(oi, oj, A0.y, A0.z, A1.y, A1.z, B0.y, B0.z, B1.y, B1.z);
+            double *pe = pf + (s ? g.cs : 0), *po = pf + (s ? 0 : g.cs);
+            if (v2)
+                st2(pe, __dadd_rn(fe.x, e0), __dadd_rn(fe.y, e1));
+            else
+                pe[0] = __dadd_rn(fe.x, e0);
+            if (v3)
+                st2(po, __dadd_rn(fo.x, o0), __dadd_rn(fo.y, o1));
+            else if (v1)
+                po[0] = __dadd_rn(fo.x, o0);
+        }
+        c_s = c_s + 1 == S ? 0 : c_s + 1;
+        pf += g.pj;
+        __syncthreads();
+        issue_upto(t);
+    };
+    for (int t = ia; t < ib; t += 2) {
+        const bool has_odd = t + 1 < ib;
+        if (work && has_odd) {  // coarse plane I+1: requested now, used by the odd plane
+            B0 = t_ld_c3(gc, ec, I + 1, J0, mq);
+            B1 = oj ? t_ld_c3(gc, ec, I + 1, J0 + 1, mq) : B0;
+        }
+        plane(t, 0);
+        if (has_odd) {
+            plane(t + 1, 1);
+            A0 = B0;
+            A1 = B1;
+            I++;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
 // host side: tile shapes and launches
 // ---------------------------------------------------------------------------
 namespace {
@@ -1094,6 +1274,61 @@ bool launch_tile_half_sweep(const Geo &g, double *v, const double *d, double hSq
         if (fixed) k_tile_sweep<0, 6, 43><<<c.grid, c.threads, c.smem, st>>>(c.p, tm_v, tm_d);
         else k_tile_sweep<0, 0, 0><<<c.grid, c.threads, c.smem, st>>>(c.p, tm_v, tm_d);
     }
+    ++*launch_counter();
+    return true;
+}
+
+// prolongation + correction of local fine planes [il_lo, il_hi) through the TMA ring
+bool launch_tile_prolong(const Geo &gc, const double *ec, const Geo &gf, double *ef, int il_lo,
+                         int il_hi, cudaStream_t st)
+{
+    static const int on = env_int("MGB_TILE_PROLONG", 1);
+    static const long long min_plane = env_int("MGB_TILE_PROLONG_MIN_PLANE", 200000);
+    if (!on || !tile_enabled() || il_hi - il_lo < 8 || !tile_worthwhile(gf) ||
+        ((long long)gf.nj * gf.nk < min_plane && g_tile_min_plane > 0) || ((gf.i0 + il_lo) & 1))
+        return false;
+    TileCfg c{};
+    const int rows = env_int("MGB_TILE_PROLONG_R", 6), qcap = env_int("MGB_TILE_PROLONG_Q", 43);
+    TileP &p = c.p;
+    p.gf = gf;
+    p.gc = gc;
+    const int nq = (gf.nk + 3) / 4;
+    p.TQo = p.TQt = even_tile(nq, qcap);
+    p.TRo = p.TRt = even_tile(gf.nj, rows);
+    c.grid.x = (nq + p.TQo - 1) / p.TQo;
+    c.grid.y = (gf.nj + p.TRo - 1) / p.TRo;
+    const int nplanes = il_hi - il_lo;
+    const long long per_layer = (long long)c.grid.x * c.grid.y;
+    int want = (int)((16LL * 148 + per_layer - 1) / per_layer);
+    int maxch = nplanes / env_int("MGB_TILE_MINCHUNK", 24);
+    if (maxch < 1) maxch = 1;
+    if (want > maxch) want = maxch;
+    if (want < 1) want = 1;
+    p.chunk = (nplanes + want - 1) / want;
+    p.chunk += p.chunk & 1;  // whole (even, odd) pairs
+    c.grid.z = (nplanes + p.chunk - 1) / p.chunk;
+    p.p_lo = il_lo;
+    p.p_hi = il_hi;
+    c.threads = ((p.TRt * p.TQt + 31) / 32) * 32;
+    const size_t RS = p.TRt + 2, PW = 2 * (p.TQt + 2);
+    const size_t slot_d = (2 * RS * PW + 15) & ~(size_t)15;
+    c.smem = 128 + 4 * slot_d * 8;
+    if (c.threads > 384 || c.smem > 112 * 1024 || c.grid.z > 65535 || c.grid.y > 65535)
+        return false;
+    p.v = ef; p.vw = ef; p.d = nullptr; p.hSq = 0.; p.invHsq = 0.;
+    CUtensorMap tm_v;
+    if (!make_tensor_map(&tm_v, gf, ef, (int)PW, (int)RS, 2))
+        return false;
+    static bool attr = false;
+    if (!attr) {
+        cudaFuncSetAttribute(k_tile_prolong<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024);
+        cudaFuncSetAttribute(k_tile_prolong<6, 43>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024);
+        attr = true;
+    }
+    if (p.TRt == 6 && p.TQt == 43)
+        k_tile_prolong<6, 43><<<c.grid, c.threads, c.smem, st>>>(c.p, ec, tm_v);
+    else
+        k_tile_prolong<0, 0><<<c.grid, c.threads, c.smem, st>>>(c.p, ec, tm_v);
     ++*launch_counter();
     return true;
 }
