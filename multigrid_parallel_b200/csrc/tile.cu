@@ -980,6 +980,28 @@ int tile_bps();
 size_t tile_smem_cap();
 int tile_max_threads();
 
+// Number of plane chunks (grid.z).  Measured on B200 (513^3, 1025^3): chunks of
+// about 52 fine planes are best -- 341-plane chunks at 1025^3 cost 10-20 %,
+// 24-plane chunks at 513^3 2-4 % (each chunk re-reads 2-4 planes to start up) --
+// as long as the launch still has >= 4 blocks per resident slot; never fewer
+// than `minchunk` fine planes per chunk.  `unit` = fine planes per counted plane.
+int plan_chunks(int nplanes, int unit, long long per_layer, int minchunk)
+{
+    static const int target = env_int("MGB_TILE_CHUNK", 52);
+    long long want = ((long long)nplanes * unit + target / 2) / target;
+    const long long fill = (4LL * 296 + per_layer - 1) / per_layer;
+    if (want < fill)
+        want = fill;
+    long long maxch = (long long)nplanes * unit / minchunk;
+    if (maxch < 1)
+        maxch = 1;
+    if (want > maxch)
+        want = maxch;
+    if (want < 1)
+        want = 1;
+    return (int)want;
+}
+
 // split n units into the fewest tiles of at most `cap` units, evenly
 int even_tile(int n, int cap)
 {
@@ -1018,18 +1040,9 @@ bool shape_cfg(TileCfg &c, const Geo &gf, bool sweep, bool restr, const Geo *gc,
     p.p_lo = p_lo;
     p.p_hi = p_hi;
     const int nplanes = p_hi - p_lo;
-    // chunks of planes: enough blocks for ~16 waves over the SMs, but chunks of at
-    // least `minchunk` fine planes (every chunk re-reads 2-4 planes to start up)
     const int unit = restr ? 2 : 1;  // a coarse plane is two fine planes
     const long long per_layer = (long long)c.grid.x * c.grid.y;
-    int want = (int)((16LL * 148 + per_layer - 1) / per_layer);
-    int maxch = nplanes * unit / minchunk;
-    if (maxch < 1)
-        maxch = 1;
-    if (want > maxch)
-        want = maxch;
-    if (want < 1)
-        want = 1;
+    const int want = plan_chunks(nplanes, unit, per_layer, minchunk);
     p.chunk = (nplanes + want - 1) / want;
     c.grid.z = (nplanes + p.chunk - 1) / p.chunk;
     c.threads = ((p.TRt * p.TQt + 31) / 32) * 32;
@@ -1238,11 +1251,7 @@ bool launch_tile_half_sweep(const Geo &g, double *v, const double *d, double hSq
     c.grid.y = (g.nj + p.TRo - 1) / p.TRo;
     const int nplanes = il_hi - il_lo;
     const long long per_layer = (long long)c.grid.x * c.grid.y;
-    int want = (int)((16LL * 148 + per_layer - 1) / per_layer);
-    int maxch = nplanes / env_int("MGB_TILE_MINCHUNK", 24);
-    if (maxch < 1) maxch = 1;
-    if (want > maxch) want = maxch;
-    if (want < 1) want = 1;
+    const int want = plan_chunks(nplanes, 1, per_layer, env_int("MGB_TILE_MINCHUNK", 24));
     p.chunk = (nplanes + want - 1) / want;
     c.grid.z = (nplanes + p.chunk - 1) / p.chunk;
     p.p_lo = il_lo;
@@ -1299,11 +1308,7 @@ bool launch_tile_prolong(const Geo &gc, const double *ec, const Geo &gf, double 
     c.grid.y = (gf.nj + p.TRo - 1) / p.TRo;
     const int nplanes = il_hi - il_lo;
     const long long per_layer = (long long)c.grid.x * c.grid.y;
-    int want = (int)((16LL * 148 + per_layer - 1) / per_layer);
-    int maxch = nplanes / env_int("MGB_TILE_MINCHUNK", 24);
-    if (maxch < 1) maxch = 1;
-    if (want > maxch) want = maxch;
-    if (want < 1) want = 1;
+    const int want = plan_chunks(nplanes, 1, per_layer, env_int("MGB_TILE_MINCHUNK", 24));
     p.chunk = (nplanes + want - 1) / want;
     p.chunk += p.chunk & 1;  // whole (even, odd) pairs
     c.grid.z = (nplanes + p.chunk - 1) / p.chunk;
