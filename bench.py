@@ -36,7 +36,7 @@ HALF_SWEEP_BYTES_PER_DOF = 12.0       # read 1/2 v, read 1/2 d, wri
 # SURVEY 8(d) algorithmic bytes per DOF of the other finest-level stages
 # stage -> (kernel as named in profiles/traffic.json, what it is, bytes per DOF)
 STAGE_BYTES_PER_DOF = {"CalcResidual1": ("k_tile<-1,1,2,11,34>", "residual+restrict (TMA tile kernel)", 17.0),
-                       "Prolongate&Correct": ("k_prolong_correct8", "prolongation+correction", 17.0),
+                       "Prolongate&Correct": ("k_tile_prolong<6,43>", "prolongation+correction (TMA ring)", 17.0),
                        "CalcResidual2": ("k_tile<-1,0,2,5,43>", "residual norm (TMA tile kernel)", 16.0)}
 
 
@@ -295,8 +295,8 @@ def run_ours(args):
                 "d2h_bytes_per_step": int(dof * 8), "seconds_per_solve": t_e2e, "cycles": cycles,
                 "step": "one full solve: upload grid+rhs from pinned host memory, V-cycles to "
                         "1e-8*||d||, download grid"},
-        "roofline": {"bound": "hbm", "kernel": "k_half_sweep_pipe", "achieved": achieved, "peak": peak,
-                     "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic("k_half_sweep_pipe"),
+        "roofline": {"bound": "hbm", "kernel": "k_tile_sweep (RB-GS half-sweep, TMA ring)", "achieved": achieved, "peak": peak,
+                     "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic("k_tile_sweep<1,6,43>"),
                      "peak_source": peak_src, "bytes_per_dof": HALF_SWEEP_BYTES_PER_DOF,
                      "avg_launch_us": t_half * 1e6, "share_of_finest_level": share,
                      "frac_of_8TBs_nominal": achieved / 8000.0,
