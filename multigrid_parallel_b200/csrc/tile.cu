@@ -37,10 +37,12 @@
 //
 // Algorithmic HBM traffic per fine DOF: norm 16 B, +restrict 17 B, and the
 // fused half-sweep comes for free (16 / 17 B instead of 12 + 16 / 12 + 17).
-// Measured on B200 at 513^3 (round 1): norm 352 us = 94 % of the measured HBM
-// copy peak; +restrict 618 us (issue-bound: 4 points per thread and barrier
-// interval); the sweep-fused forms are correct but still issue-bound and slower
-// than their unfused pairs, so the V-cycle uses them only with MGB_OPT_FUSE=2.
+// Measured on B200 at 513^3 (round 1 end): norm 330 us = 99 % of the measured HBM
+// copy peak; +restrict 500 us (issue-bound: 4 points per thread and barrier
+// interval); the sweep-fused forms are correct but issue-bound and slower than
+// their unfused pairs, so the V-cycle uses them only with MGB_OPT_FUSE=2.
+// Further down: the half-sweep itself (k_tile_sweep, 249 us = 99 %) and the
+// prolongation (k_tile_prolong, 415 us = 84 %) on the same ring.
 // All arithmetic is the reference's, in its order, with explicitly rounded
 // intrinsics: results are bit-identical to the unfused kernels.
 #include <cuda.h>  // CUtensorMap (types only; the encoder is fetched at run time)
