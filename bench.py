@@ -136,6 +136,13 @@ def cpu_reference_cycles(coarse, levels, gs, warm, timed):
         raise RuntimeError("oracle/_ref/libmg_ref.so missing (built by __graft_entry__.build() "
                            "where /root/reference exists)")
     L = ref.L
+    # all the host threads this process may use (torchrun exports OMP_NUM_THREADS=1,
+    # which would silently turn the OpenMP reference into a serial run)
+    try:
+        ncores = len(os.sched_getaffinity(0))
+    except AttributeError:
+        ncores = os.cpu_count() or 1
+    ref.set_threads(ncores)
     grid, rhs, h = c_dp(), c_dp(), C.c_double()
     N = L.ref_solver_open(coarse, levels, gs, C.byref(grid), C.byref(rhs), C.byref(h))
     # test_mg_3d.c:17-29 set-up
@@ -168,7 +175,10 @@ def run_reference(args):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
         "config": {"workload": f"test_mg_3d {COARSE} {LEVELS} {GS}: {N}^3 fp64 Laplace V(2,2)-cycle, "
-                               "reference OpenMP code on host cores"},
+                               "reference OpenMP code on host cores"
+                               + ("" if args.gpus == 1 else f" (the reference only has cubes: this is one "
+                                  f"rank's 513^3 share of the {args.gpus}-GPU arm's (512*N+1)x513x513 box; "
+                                  "the metric is per DOF)")},
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "reference",
                          "sample": f"{args.steps} V-cycles of the {N}^3 problem after {args.warmup} warm-up"},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
