@@ -991,7 +991,7 @@ int plan_chunks(int nplanes, int unit, long long per_layer, int minchunk)
 {
     static const int target = env_int("MGB_TILE_CHUNK", 52);
     long long want = ((long long)nplanes * unit + target / 2) / target;
-    const long long fill = (4LL * 296 + per_layer - 1) / per_layer;
+    const long long fill = ((long long)env_int("MGB_TILE_FILL", 6) * 296 + per_layer - 1) / per_layer;
     if (want < fill)
         want = fill;
     long long maxch = (long long)nplanes * unit / minchunk;
