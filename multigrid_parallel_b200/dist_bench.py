@@ -59,6 +59,37 @@ def run(args, rank, world, local_rank):
     clocks = sampler.finish() if sampler else None
     value = dof * args.steps / dt
 
+    # dominant kernel per GPU: the RB-GS half-sweep on this rank's slab of the finest
+    # level, timed with its halo step (push + wait) as the cycle runs it
+    import json as _json
+    import os as _os
+    try:
+        peak = float(_json.load(open(_os.path.join(_os.path.dirname(_os.path.dirname(
+            _os.path.abspath(__file__))), "MEASURED_PEAKS.json")))["hbm_gbs"])
+        peak_src = "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    for _ in range(2):
+        s.half_sweep(top, 1)
+        s.half_sweep(top, 0)
+    s.sync()
+    D.barrier()
+    s.timer_start()
+    nrep = 10
+    for _ in range(nrep):
+        s.half_sweep(top, 1)
+        s.half_sweep(top, 0)
+    t_half = D.max_over_ranks(s.timer_stop()) / (2 * nrep)
+    own_planes = own_hi - own_lo
+    local_dof = float(own_planes) * nj * nk
+    achieved = 12.0 * local_dof / t_half / 1e9
+    roofline = {"bound": "hbm", "kernel": "k_tile_sweep (RB-GS half-sweep, TMA ring) + halo step",
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "peak_source": peak_src, "bytes_per_dof": 12.0,
+                "avg_launch_us": t_half * 1e6,
+                "note": f"per GPU, rank {rank}'s slab of {own_planes} planes; time = slowest rank, "
+                        "half-sweep kernel plus its P2P halo push + wait"}
+
     if strong:
         fresh()
         hist = s.solve(init * TOL, 100)
@@ -89,7 +120,7 @@ def run(args, rank, world, local_rank):
                                           if world > 1 else "single GPU",
                            "l2": "inputs larger than L2", "cycles_to_1e-8": len(hist),
                            "final_residual": float(hist[-1])},
-                "clocks": clocks, "gpu_launches": int(launches), "e2e": None, "roofline": None,
+                "clocks": clocks, "gpu_launches": int(launches), "e2e": None, "roofline": roofline,
                 "cpu_baseline": None}), flush=True)
         D.barrier()
         s.close()
@@ -137,7 +168,7 @@ def run(args, rank, world, local_rank):
                     "cycles": cycles,
                     "step": "one full solve: every rank uploads its grid+rhs slab from pinned host "
                             "memory, V-cycles to 1e-8*||d||, every rank downloads its slab"},
-            "roofline": None, "cpu_baseline": None,
+            "roofline": roofline, "cpu_baseline": None,
         }
         print(json.dumps(line), flush=True)
     D.barrier()
