@@ -73,6 +73,13 @@ enum {
     MGB_G_TILE_MIN_PLANE = 1  /* use them on levels with nj*nk >= value (default 40000)         */
 };
 int mgb_set_global(int key, long long value);
+/* the launch plan the TMA tile kernels would use on an ni x nj x nk level, without
+ * launching anything (works without a GPU; used by the CPU-side tests): kind 0
+ * residual norm, 1 residual+restrict (into the (n+1)/2 level), 2 half-sweep,
+ * 3 prolongation; out12 = {ok, grid.x, grid.y, grid.z, threads, dynamic smem
+ * bytes, tile rows, tile quads, rows advance, quads advance, coarse rows per
+ * tile, planes per chunk} */
+int mgb_tile_plan(int kind, int ni, int nj, int nk, long long *out12);
 int mgb_sync(mgb_solver *s);
 
 /* ---- level arrays: the reference hands out raw host pointers u[l], d[l],

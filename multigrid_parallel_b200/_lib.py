@@ -56,6 +56,7 @@ def load_library():
     L.mgb_set_option.argtypes = [vp, i, i]
     L.mgb_sync.argtypes = [vp]
     L.mgb_set_global.argtypes = [i, C.c_longlong]
+    L.mgb_tile_plan.argtypes = [i, i, i, i, C.POINTER(C.c_longlong)]
     L.mgb_upload.argtypes = [vp, i, i, C.c_void_p]
     L.mgb_download.argtypes = [vp, i, i, C.c_void_p]
     L.mgb_zero.argtypes = [vp, i, i]

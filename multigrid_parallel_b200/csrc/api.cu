@@ -720,6 +720,24 @@ extern "C" int mgb_set_global(int key, long long value)
     return 0;
 }
 
+extern "C" int mgb_tile_plan(int kind, int ni, int nj, int nk, long long *out12)
+{
+    if (kind < 0 || kind > 3 || ni < 3 || nj < 3 || nk < 3 || !out12)
+        return fail("mgb_tile_plan: bad arguments");
+    const Geo gf = make_geo(ni, nj, nk, ni, 0);
+    if (kind == 1) {
+        if (!(ni & 1) || !(nj & 1) || !(nk & 1))
+            return fail("mgb_tile_plan: restriction needs odd extents");
+        const Geo gc = make_geo((ni + 1) / 2, (nj + 1) / 2, (nk + 1) / 2, (ni + 1) / 2, 0);
+        tile_plan_query(1, gf, &gc, 0, gc.ni, out12);
+    } else if (kind == 3) {
+        tile_plan_query(3, gf, nullptr, 0, ni, out12);
+    } else {
+        tile_plan_query(kind, gf, nullptr, 1, ni - 1, out12);
+    }
+    return 0;
+}
+
 extern "C" int mgb_sync(mgb_solver *s)
 {
     if (bind(s))

@@ -107,6 +107,8 @@ void launch_coarse_tail(const TailP &p, cudaStream_t st);
 bool launch_tile_half_sweep(const Geo &g, double *v, const double *d, double hSq, int colour,
                             int il_lo, int il_hi, cudaStream_t st);
 
+// launch plan of a tile kernel (no launch): see tile.cu
+void tile_plan_query(int kind, const Geo &gf, const Geo *gc, int p_lo, int p_hi, long long *out);
 // prolongation + correction through the TMA ring (tile.cu); false: use launch_prolong_correct's
 // marching kernels
 bool launch_tile_prolong(const Geo &gc, const double *ec, const Geo &gf, double *ef, int il_lo,

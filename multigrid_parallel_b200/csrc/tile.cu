@@ -1176,6 +1176,60 @@ bool launch_cfg(const TileCfg &c, cudaStream_t st)
 
 }  // namespace
 
+// tile plan of the sweep / prolongation kernels: tiles partition rows and quads
+// (no halo threads), 4 ring slots of `ncol` colours; `pairs`: chunks hold whole
+// (even, odd) plane pairs
+static bool plan_simple(TileCfg &c, const Geo &g, int il_lo, int il_hi, int rows, int qcap,
+                        int ncol, bool pairs)
+{
+    TileP &p = c.p;
+    p.gf = g;
+    const int nq = (g.nk + 3) / 4;
+    p.TQo = p.TQt = even_tile(nq, qcap);
+    p.TRo = p.TRt = even_tile(g.nj, rows);
+    p.TY = 0;
+    c.grid.x = (nq + p.TQo - 1) / p.TQo;
+    c.grid.y = (g.nj + p.TRo - 1) / p.TRo;
+    const int nplanes = il_hi - il_lo;
+    const long long per_layer = (long long)c.grid.x * c.grid.y;
+    const int want = plan_chunks(nplanes, 1, per_layer, env_int("MGB_TILE_MINCHUNK", 24));
+    p.chunk = (nplanes + want - 1) / want;
+    if (pairs)
+        p.chunk += p.chunk & 1;
+    c.grid.z = (nplanes + p.chunk - 1) / p.chunk;
+    p.p_lo = il_lo;
+    p.p_hi = il_hi;
+    c.threads = ((p.TRt * p.TQt + 31) / 32) * 32;
+    const size_t RS = p.TRt + 2, PW = 2 * (p.TQt + 2);
+    const size_t slot_d = ((size_t)ncol * RS * PW + 15) & ~(size_t)15;
+    c.smem = 128 + 4 * slot_d * 8;
+    c.ok = nplanes >= 1 && c.threads <= 384 && c.smem <= 112 * 1024 && c.grid.z <= 65535 &&
+           c.grid.y <= 65535;
+    return c.ok;
+}
+
+// the launch plan of a tile kernel without launching it (CPU-side tests):
+// kind 0 residual norm, 1 residual+restrict, 2 half-sweep, 3 prolongation;
+// out = {ok, grid.x, grid.y, grid.z, threads, smem bytes, TRt, TQt, TRo, TQo, TY, chunk}
+void tile_plan_query(int kind, const Geo &gf, const Geo *gc, int p_lo, int p_hi, long long *out)
+{
+    TileCfg c{};
+    if (kind == 0)
+        c = make_cfg(gf, false, false, nullptr, p_lo, p_hi);
+    else if (kind == 1)
+        c = make_cfg(gf, false, true, gc, p_lo, p_hi);
+    else if (kind == 2)
+        plan_simple(c, gf, p_lo, p_hi, env_int("MGB_TILE_SWEEP_R", 6), env_int("MGB_TILE_SWEEP_Q", 43),
+                    1, false);
+    else
+        plan_simple(c, gf, p_lo, p_hi, env_int("MGB_TILE_PROLONG_R", 6),
+                    env_int("MGB_TILE_PROLONG_Q", 43), 2, true);
+    const long long v[12] = {c.ok, c.grid.x, c.grid.y, c.grid.z, c.threads, (long long)c.smem,
+                             c.p.TRt, c.p.TQt, c.p.TRo, c.p.TQo, c.p.TY, c.p.chunk};
+    for (int i = 0; i < 12; i++)
+        out[i] = v[i];
+}
+
 // process-wide switches (mgb_set_global): tile kernels on/off, and the smallest
 // plane (points) they are used for -- below it a level is latency-bound and the
 // plain kernels (no ring start-up) are faster
@@ -1243,27 +1297,11 @@ bool launch_tile_half_sweep(const Geo &g, double *v, const double *d, double hSq
         ((long long)g.nj * g.nk < min_plane && g_tile_min_plane > 0))
         return false;
     TileCfg c{};
-    const int rows = env_int("MGB_TILE_SWEEP_R", 6), qcap = env_int("MGB_TILE_SWEEP_Q", 43);
-    TileP &p = c.p;
-    p.gf = g;
-    const int nq = (g.nk + 3) / 4;
-    p.TQo = p.TQt = even_tile(nq, qcap);
-    p.TRo = p.TRt = even_tile(g.nj, rows);
-    c.grid.x = (nq + p.TQo - 1) / p.TQo;
-    c.grid.y = (g.nj + p.TRo - 1) / p.TRo;
-    const int nplanes = il_hi - il_lo;
-    const long long per_layer = (long long)c.grid.x * c.grid.y;
-    const int want = plan_chunks(nplanes, 1, per_layer, env_int("MGB_TILE_MINCHUNK", 24));
-    p.chunk = (nplanes + want - 1) / want;
-    c.grid.z = (nplanes + p.chunk - 1) / p.chunk;
-    p.p_lo = il_lo;
-    p.p_hi = il_hi;
-    c.threads = ((p.TRt * p.TQt + 31) / 32) * 32;
-    const size_t RS = p.TRt + 2, PW = 2 * (p.TQt + 2);
-    const size_t slot_d = (RS * PW + 15) & ~(size_t)15;
-    c.smem = 128 + 4 * slot_d * 8;
-    if (c.threads > 384 || c.smem > 112 * 1024 || c.grid.z > 65535 || c.grid.y > 65535)
+    if (!plan_simple(c, g, il_lo, il_hi, env_int("MGB_TILE_SWEEP_R", 6),
+                     env_int("MGB_TILE_SWEEP_Q", 43), 1, false))
         return false;
+    TileP &p = c.p;
+    const size_t RS = p.TRt + 2, PW = 2 * (p.TQt + 2);
     p.v = v; p.vw = v; p.d = d; p.hSq = hSq; p.invHsq = 0.;
     CUtensorMap tm_v, tm_d;
     if (!make_tensor_map(&tm_v, g, v, (int)PW, (int)RS, 1) ||
@@ -1299,29 +1337,12 @@ bool launch_tile_prolong(const Geo &gc, const double *ec, const Geo &gf, double 
         ((long long)gf.nj * gf.nk < min_plane && g_tile_min_plane > 0) || ((gf.i0 + il_lo) & 1))
         return false;
     TileCfg c{};
-    const int rows = env_int("MGB_TILE_PROLONG_R", 6), qcap = env_int("MGB_TILE_PROLONG_Q", 43);
-    TileP &p = c.p;
-    p.gf = gf;
-    p.gc = gc;
-    const int nq = (gf.nk + 3) / 4;
-    p.TQo = p.TQt = even_tile(nq, qcap);
-    p.TRo = p.TRt = even_tile(gf.nj, rows);
-    c.grid.x = (nq + p.TQo - 1) / p.TQo;
-    c.grid.y = (gf.nj + p.TRo - 1) / p.TRo;
-    const int nplanes = il_hi - il_lo;
-    const long long per_layer = (long long)c.grid.x * c.grid.y;
-    const int want = plan_chunks(nplanes, 1, per_layer, env_int("MGB_TILE_MINCHUNK", 24));
-    p.chunk = (nplanes + want - 1) / want;
-    p.chunk += p.chunk & 1;  // whole (even, odd) pairs
-    c.grid.z = (nplanes + p.chunk - 1) / p.chunk;
-    p.p_lo = il_lo;
-    p.p_hi = il_hi;
-    c.threads = ((p.TRt * p.TQt + 31) / 32) * 32;
-    const size_t RS = p.TRt + 2, PW = 2 * (p.TQt + 2);
-    const size_t slot_d = (2 * RS * PW + 15) & ~(size_t)15;
-    c.smem = 128 + 4 * slot_d * 8;
-    if (c.threads > 384 || c.smem > 112 * 1024 || c.grid.z > 65535 || c.grid.y > 65535)
+    if (!plan_simple(c, gf, il_lo, il_hi, env_int("MGB_TILE_PROLONG_R", 6),
+                     env_int("MGB_TILE_PROLONG_Q", 43), 2, true))
         return false;
+    TileP &p = c.p;
+    p.gc = gc;
+    const size_t RS = p.TRt + 2, PW = 2 * (p.TQt + 2);
     p.v = ef; p.vw = ef; p.d = nullptr; p.hSq = 0.; p.invHsq = 0.;
     CUtensorMap tm_v;
     if (!make_tensor_map(&tm_v, gf, ef, (int)PW, (int)RS, 2))
