@@ -43,7 +43,9 @@ enum {                                             /* mgb_set_option keys */
                              * residual+restriction, r not stored; 2: also the last colour
                              * of each smoother leg inside the residual kernel that follows */
     MGB_OPT_GRAPH_LEVELS = 3,/* only levels < this are graphed when PROFILE=1              */
-    MGB_OPT_TAIL = 4        /* 1 (default): the levels of <= ~17^3 points run as ONE kernel */
+    MGB_OPT_TAIL = 4,       /* 1 (default): the levels of <= ~17^3 points run as ONE kernel */
+    MGB_OPT_ZERO_GUESS = 5  /* 1 (default): coarse levels are not zeroed before pre-smoothing,
+                             * their first half-sweep takes the zero guess as given       */
 };
 
 /* ---- errors / device ---------------------------------------------------- */

@@ -140,6 +140,12 @@ struct mgb_solver {
     int opt_graph = 1, opt_profile = 0, opt_fuse = 1;
     // levels 0..tail_top (<= ~33^3) run as ONE kernel (tail.cu); -1: none
     int opt_tail = 1, tail_top = -1;
+    // coarse levels are not zeroed before pre-smoothing: their first half-sweep
+    // takes the guess as 0 (launch_first_sweep_zero).  That needs the faces and
+    // pads of the coarse u arrays to BE zero, which the cycle itself maintains;
+    // API calls that can break it set coarse_dirty, and the next cycle zeroes once.
+    int opt_zero_guess = 1;
+    bool coarse_dirty = false;
     cudaGraphExec_t gexec = nullptr;
     long long graph_launches = 0;
     int eager_cycles = 0;  // partitioned solver: cycles run eagerly before the capture
@@ -528,6 +534,8 @@ static int create_impl(mgb_solver **out, int ci, int cj, int ck, int levels, int
         const long long max_pts = getenv("MGB_TAIL_POINTS") ? atoll(getenv("MGB_TAIL_POINTS")) : 5000;
         if (getenv("MGB_TAIL"))
             s->opt_tail = atoi(getenv("MGB_TAIL")) != 0;
+        if (getenv("MGB_ZERO_GUESS"))
+            s->opt_zero_guess = atoi(getenv("MGB_ZERO_GUESS")) != 0;
         const int lim = nranks > 1 ? s->LD - 1 : levels - 2;  // strictly coarse, on one GPU
         for (int l = 0; l <= lim && l < 8; l++) {
             const Geo &g = s->lv[l].g;
@@ -705,6 +713,10 @@ extern "C" int mgb_set_option(mgb_solver *s, int key, int value)
         s->opt_tail = value != 0;
         drop_graph(s);
         break;
+    case MGB_OPT_ZERO_GUESS:
+        s->opt_zero_guess = value != 0;
+        drop_graph(s);
+        break;
     default: return fail("unknown option %d", key);
     }
     return 0;
@@ -773,6 +785,8 @@ extern "C" int mgb_upload(mgb_solver *s, int level, int which, const double *hos
     if (!host)
         return fail("host pointer is null");
     Level &lv = s->lv[level];
+    if (level < s->L - 1)
+        s->coarse_dirty = true;  // may put non-zero values on a coarse level's faces
     const size_t n = (size_t)lv.g.li * lv.g.nj * lv.g.nk;  // local planes [i0, i0+li)
     if (need_stage(s, n))
         return 1;
@@ -818,6 +832,8 @@ extern "C" int mgb_set_dirichlet(mgb_solver *s, int level, int which)
     if (bind(s) || check_level(s, level, which))
         return 1;
     Level &lv = s->lv[level];
+    if (level < s->L - 1)
+        s->coarse_dirty = true;
     LaunchScope ls(s);
     launch_set_dirichlet(lv.g, lv.a[which].base, lv.h, s->st);
     halo_fence(s, lv);
@@ -1037,12 +1053,18 @@ extern "C" int mgb_error_sumsq(mgb_solver *s, double *sumsq)
 // ----------------------------------------------------------------------------
 // operators (enqueue only; the caller of the C entry point synchronises)
 // ----------------------------------------------------------------------------
-static void q_half_sweep(mgb_solver *s, int q, int colour)
+static void q_half_sweep(mgb_solver *s, int q, int colour, bool zero_guess = false)
 {
     if (!s->works_on(q))
         return;
     Level &lv = s->lv[q];
     const int lo = lv.sweep_lo(), hi = lv.sweep_hi();
+    if (zero_guess) {
+        launch_first_sweep_zero(lv.g, lv.a[MGB_U].base, lv.a[MGB_D].base, lv.hSq, colour, lo, hi,
+                                s->st);
+        halo_after_sweep(s, lv, colour);
+        return;
+    }
     // worth it only where the interior of the sweep outlasts the exchange by far:
     // >= 4M points per slab (off by default: MGB_OVERLAP=1)
     if (lv.dist && s->opt_overlap && hi - lo >= 4 &&
@@ -1072,10 +1094,10 @@ static void q_half_sweep(mgb_solver *s, int q, int colour)
     halo_after_sweep(s, lv, colour);
 }
 
-static void q_smooth(mgb_solver *s, int q, int iters, int first_red)
+static void q_smooth(mgb_solver *s, int q, int iters, int first_red, bool zero_guess = false)
 {
     for (int it = 0; it < iters; it++) {
-        q_half_sweep(s, q, first_red ? 1 : 0);
+        q_half_sweep(s, q, first_red ? 1 : 0, zero_guess && it == 0);
         q_half_sweep(s, q, first_red ? 0 : 1);
     }
 }
@@ -1259,6 +1281,7 @@ extern "C" int mgb_residual(mgb_solver *s, int level, int store_r, double *sumsq
 extern "C" int mgb_restrict(mgb_solver *s, int level)
 {
     OP_PROLOGUE(level, 1);
+    s->coarse_dirty = true;  // injects whatever sits on r's faces
     if (s->is_dist())
         return fail("the partitioned solver only has the fused residual+restriction");
     q_restrict(s, level);
@@ -1310,6 +1333,7 @@ extern "C" int mgb_coarse_solve(mgb_solver *s)
         return 1;
     if (!s->lu)
         return fail("no coarse operator (single-grid session)");
+    s->coarse_dirty = true;  // u[0]'s faces become d[0]'s
     LaunchScope ls(s);
     q_coarse_solve(s);
     CKLAUNCH();
@@ -1391,7 +1415,11 @@ static void enqueue_cycle(mgb_solver *s, int q, bool timed)
         launch_coarse_tail(p, s->st);
         return;
     }
-    if (q < s->L - 1) {  // 1254-1260: coarse levels start from a zero guess
+    // 1254-1260: coarse levels start from a zero guess.  With at least one
+    // smoothing iteration the level is not zeroed: its first half-sweep treats
+    // the guess as 0 and the second one overwrites the other colour
+    const bool zero_guess = q > 0 && q < s->L - 1 && s->opt_zero_guess && s->gs >= 1;
+    if (q < s->L - 1 && !zero_guess && q > 0) {
         cudaMemsetAsync(lv.a[MGB_U].base, 0, sizeof(double) * 2 * lv.g.cs, s->st);
         halo_fence(s, lv);
     }
@@ -1406,10 +1434,10 @@ static void enqueue_cycle(mgb_solver *s, int q, bool timed)
     {
         StageTimer t(s, timed, q, MGB_ST_SMOOTH1);  // 1282
         if (fuse_sweep) {
-            q_smooth(s, q, s->gs - 1, 1);
-            q_half_sweep(s, q, 1);
+            q_smooth(s, q, s->gs - 1, 1, zero_guess);
+            q_half_sweep(s, q, 1, zero_guess && s->gs == 1);
         } else {
-            q_smooth(s, q, s->gs, 1);
+            q_smooth(s, q, s->gs, 1, zero_guess);
         }
     }
     if (s->opt_fuse) {
@@ -1497,6 +1525,18 @@ extern "C" int mgb_vcycle(mgb_solver *s, double *sumsq)
         return fail("no coarse operator");
     if (s->L < 2)
         return fail("a V-cycle needs at least 2 levels");
+    if (s->coarse_dirty) {
+        // direct array / operator calls may have left non-zero values on the faces of
+        // coarse u arrays; the cycle (which no longer zeroes them every time) needs 0
+        for (int q = 0; q < s->L - 1; q++) {
+            Level &lv = s->lv[q];
+            if (!s->works_on(q))
+                continue;
+            CK(cudaMemsetAsync(lv.a[MGB_U].base, 0, sizeof(double) * 2 * lv.g.cs, s->st));
+            halo_fence(s, lv);
+        }
+        s->coarse_dirty = false;
+    }
     if (s->opt_profile) {
         // eager launches bracketed by CUDA events per level and stage
         const long long before = launches_issued();

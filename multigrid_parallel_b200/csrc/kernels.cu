@@ -380,6 +380,57 @@ k_half_sweep_pipe(Geo g, const double *__restrict__ vo, double *__restrict__ vc,
     }
 }
 
+// First half-sweep of a level whose guess is identically zero (mg_3d.h:1258-1259
+// zeroes every coarse level before pre-smoothing): the six neighbours are 0, so
+// the update needs the rhs only -- same operations as gs_point with zeros, hence
+// the same bits -- and the level does not have to be zeroed first: its interior
+// is overwritten by this and the next colour's sweep, its faces and pads stay 0.
+template <int COLOUR>
+__global__ void __launch_bounds__(256)
+k_first_sweep_zero(Geo g, double *__restrict__ vc, const double *__restrict__ dc, double hSq,
+                   int il_lo, int il_hi)
+{
+    const int npair = g.kh >> 1;
+    const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= (g.pj >> 1))
+        return;
+    const int j = (int)(q / npair);
+    if (j < 1 || j > g.nj - 2)
+        return;
+    const int mp = (int)(q - (long long)j * npair);
+    const int il = il_lo + blockIdx.y;
+    if (il >= il_hi)
+        return;
+    const long long idx = (long long)il * g.pj + 2 * q;
+    const double2 dd = ld2(dc + idx);
+    const double sixth = 1. / 6;
+    const double r0 = gs_point(0., 0., 0., 0., 0., 0., hSq, dd.x, sixth);
+    const double r1 = gs_point(0., 0., 0., 0., 0., 0., hSq, dd.y, sixth);
+    const int kp = (COLOUR ^ (g.i0 + il + j)) & 1;
+    const int k0 = 4 * mp + kp, k1 = k0 + 2, kmax = g.nk - 2;
+    const bool ok0 = k0 >= 1 && k0 <= kmax, ok1 = k1 <= kmax;
+    if (ok0 && ok1)
+        st2(vc + idx, r0, r1);
+    else if (ok0)
+        vc[idx] = r0;
+    else if (ok1)
+        vc[idx + 1] = r1;
+}
+
+void launch_first_sweep_zero(const Geo &g, double *v, const double *d, double hSq, int colour,
+                             int il_lo, int il_hi, cudaStream_t st)
+{
+    if (il_hi <= il_lo)
+        return;
+    const long long pairs = (long long)g.pj / 2;
+    const dim3 grid((unsigned)((pairs + 255) / 256), (unsigned)(il_hi - il_lo));
+    if (colour)
+        k_first_sweep_zero<1><<<grid, 256, 0, st>>>(g, v + g.cs, d + g.cs, hSq, il_lo, il_hi);
+    else
+        k_first_sweep_zero<0><<<grid, 256, 0, st>>>(g, v, d, hSq, il_lo, il_hi);
+    COUNT_LAUNCH();
+}
+
 void launch_half_sweep(const Geo &g, double *v, const double *d, double hSq,
                        int colour, int il_lo, int il_hi, cudaStream_t st)
 {

@@ -21,6 +21,10 @@ void launch_set_dirichlet(const Geo &g, double *a, double h, cudaStream_t st);
 void launch_half_sweep(const Geo &g, double *v, const double *d, double hSq,
                        int colour, int il_lo, int il_hi, cudaStream_t st);
 
+// the same when every neighbour is known to be zero (first sweep of a coarse level)
+void launch_first_sweep_zero(const Geo &g, double *v, const double *d, double hSq, int colour,
+                             int il_lo, int il_hi, cudaStream_t st);
+
 // residual (mg_3d.h:794-842) over local planes [il_lo, il_hi); r may be
 // nullptr; the sum of squares lands in *out_sumsq (device) via `partials`
 void launch_residual(const Geo &g, const double *v, const double *d, double *r,

@@ -284,11 +284,12 @@ def test_stateless_transfer_operators(mgb, orc):
 
 
 @pytest.mark.parametrize("coarse,levels,gs", [((3, 3, 3), 5, 2), ((5, 5, 5), 3, 1), ((3, 5, 9), 4, 3)])
-@pytest.mark.parametrize("mode", ["graph", "eager", "profile", "unfused", "fuse1", "fuse2", "notail"])
+@pytest.mark.parametrize("mode", ["graph", "eager", "profile", "unfused", "fuse1", "fuse2", "notail", "nozeroguess"])
 def test_vcycle_bitwise_all_levels(mgb, orc, coarse, levels, gs, mode):
     """one and several V-cycles: every level's u and d match the oracle bit
     for bit, the returned norm to 1e-13"""
-    from multigrid_parallel_b200.solver import OPT_FUSE, OPT_GRAPH, OPT_PROFILE, OPT_TAIL
+    from multigrid_parallel_b200.solver import (OPT_FUSE, OPT_GRAPH, OPT_PROFILE, OPT_TAIL,
+                                                OPT_ZERO_GUESS)
     mg = OrcMG(orc, coarse, levels, gs)
     with _mk(mgb, coarse, levels, gs) as s:
         if mode == "eager":
@@ -303,6 +304,8 @@ def test_vcycle_bitwise_all_levels(mgb, orc, coarse, levels, gs, mode):
             s.set_option(OPT_FUSE, 2)
         elif mode == "notail":
             s.set_option(OPT_TAIL, 0)
+        elif mode == "nozeroguess":
+            s.set_option(OPT_ZERO_GUESS, 0)
         top = levels - 1
         u0, d0 = seeded(s.dims(top), 41), seeded(s.dims(top), 42)
         mg.u(top)[...] = u0
@@ -321,4 +324,34 @@ def test_vcycle_bitwise_all_levels(mgb, orc, coarse, levels, gs, mode):
             calls, secs = s.timing(top, 0)
             assert calls == 3 and secs > 0
         assert s.launch_count > 0
+        mg.close()
+
+
+@pytest.mark.parametrize("graph", [1, 0])
+def test_vcycle_after_coarse_levels_were_overwritten(mgb, orc, graph):
+    """the cycle no longer zeroes the coarse levels every time (their first
+    half-sweep takes the zero guess as given), so it relies on their faces being
+    0; arrays uploaded onto coarse levels in between (non-zero faces) must not
+    leak into the next cycle (mg_3d.h:1258-1259 zeroes them, so does the oracle)"""
+    from multigrid_parallel_b200.solver import OPT_GRAPH
+    coarse, levels, gs = (3, 3, 3), 6, 2
+    mg = OrcMG(orc, coarse, levels, gs)
+    with _mk(mgb, coarse, levels, gs) as s:
+        s.set_option(OPT_GRAPH, graph)
+        top = levels - 1
+        u0, d0 = seeded(s.dims(top), 61), seeded(s.dims(top), 62)
+        mg.u(top)[...] = u0
+        mg.d(top)[...] = d0
+        s.upload(top, mgb.MGB_U, u0)
+        s.upload(top, mgb.MGB_D, d0)
+        for cyc in range(3):
+            if cyc != 1:  # scribble over every coarse level before cycles 0 and 2
+                for lvl in range(top):
+                    s.upload(lvl, mgb.MGB_U, seeded(s.dims(lvl), 70 + lvl))
+                    s.upload(lvl, mgb.MGB_D, seeded(s.dims(lvl), 80 + lvl))
+            want = mg.vcycle()
+            got = s.vcycle()
+            assert got == pytest.approx(want, rel=NORM_RTOL), cyc
+            for lvl in range(levels):
+                assert np.array_equal(s.download(lvl, mgb.MGB_U), mg.u(lvl)), (cyc, lvl)
         mg.close()
