@@ -44,8 +44,10 @@ enum {                                             /* mgb_set_option keys */
                              * of each smoother leg inside the residual kernel that follows */
     MGB_OPT_GRAPH_LEVELS = 3,/* only levels < this are graphed when PROFILE=1              */
     MGB_OPT_TAIL = 4,       /* 1 (default): the levels of <= ~17^3 points run as ONE kernel */
-    MGB_OPT_ZERO_GUESS = 5  /* 1 (default): coarse levels are not zeroed before pre-smoothing,
+    MGB_OPT_ZERO_GUESS = 5, /* 1 (default): coarse levels are not zeroed before pre-smoothing,
                              * their first half-sweep takes the zero guess as given       */
+    MGB_OPT_PROLONG_MASK = 6/* 1 (default): inside the cycle the prolongation corrects only
+                             * the colour the post-smoother does not overwrite first      */
 };
 
 /* ---- errors / device ---------------------------------------------------- */

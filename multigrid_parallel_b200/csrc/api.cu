@@ -145,6 +145,9 @@ struct mgb_solver {
     // pads of the coarse u arrays to BE zero, which the cycle itself maintains;
     // API calls that can break it set coarse_dirty, and the next cycle zeroes once.
     int opt_zero_guess = 1;
+    // inside the cycle the prolongation corrects only the colour the post-smoother
+    // does not overwrite first (8 of its 17 B/DOF less)
+    int opt_prolong_mask = 1;
     bool coarse_dirty = false;
     cudaGraphExec_t gexec = nullptr;
     long long graph_launches = 0;
@@ -536,6 +539,8 @@ static int create_impl(mgb_solver **out, int ci, int cj, int ck, int levels, int
             s->opt_tail = atoi(getenv("MGB_TAIL")) != 0;
         if (getenv("MGB_ZERO_GUESS"))
             s->opt_zero_guess = atoi(getenv("MGB_ZERO_GUESS")) != 0;
+        if (getenv("MGB_PROLONG_MASK"))
+            s->opt_prolong_mask = atoi(getenv("MGB_PROLONG_MASK")) != 0;
         const int lim = nranks > 1 ? s->LD - 1 : levels - 2;  // strictly coarse, on one GPU
         for (int l = 0; l <= lim && l < 8; l++) {
             const Geo &g = s->lv[l].g;
@@ -715,6 +720,10 @@ extern "C" int mgb_set_option(mgb_solver *s, int key, int value)
         break;
     case MGB_OPT_ZERO_GUESS:
         s->opt_zero_guess = value != 0;
+        drop_graph(s);
+        break;
+    case MGB_OPT_PROLONG_MASK:
+        s->opt_prolong_mask = value != 0;
         drop_graph(s);
         break;
     default: return fail("unknown option %d", key);
@@ -1199,13 +1208,22 @@ static void q_residual_restrict(mgb_solver *s, int q, int colour = -1)
     }
 }
 
-static void q_prolong(mgb_solver *s, int q)
+// red_only (inside the cycle, gs >= 1): the post-smoother starts with BLACK and
+// overwrites every interior black point without reading it, so only the RED
+// points need the correction; black face points still get the reference's
+// `+= 0.` on the finest level (it turns a -0. boundary value into +0.; coarse
+// faces are +0. already)
+static void q_prolong(mgb_solver *s, int q, bool red_only = false)
 {
     if (!s->works_on(q))
         return;
     Level &f = s->lv[q], &c = s->lv[q - 1];
+    const int cmask = red_only ? 2 : 3;
     if (!f.dist) {
-        launch_prolong_correct(c.g, c.a[MGB_U].base, f.g, f.a[MGB_U].base, 0, f.g.li, s->st);
+        launch_prolong_correct(c.g, c.a[MGB_U].base, f.g, f.a[MGB_U].base, 0, f.g.li, s->st,
+                               cmask);
+        if (red_only && q == s->L - 1)
+            launch_add_zero_faces(f.g, f.a[MGB_U].base, 0, 0, f.g.li, s->st);
         return;
     }
     // owned planes plus the nearest halo plane on each side: the neighbours
@@ -1213,7 +1231,15 @@ static void q_prolong(mgb_solver *s, int q)
     const int lo = f.own_lo - (s->rank > 0 ? 1 : 0);
     const int hi = f.own_hi + (s->rank < s->nranks - 1 ? 1 : 0);
     launch_prolong_correct(c.g, c.a[MGB_U].base, f.g, f.a[MGB_U].base, lo - f.g.i0,
-                           hi - f.g.i0, s->st);
+                           hi - f.g.i0, s->st, cmask);
+    if (red_only) {
+        // only red entries of my halo planes were written, and the neighbours' next
+        // push into them is BLACK: no fence needed
+        if (q == s->L - 1)
+            launch_add_zero_faces(f.g, f.a[MGB_U].base, 0, f.own_lo - f.g.i0, f.own_hi - f.g.i0,
+                                  s->st);
+        return;
+    }
     halo_fence(s, f);
 }
 
@@ -1462,7 +1488,7 @@ static void enqueue_cycle(mgb_solver *s, int q, bool timed)
     }
     {
         StageTimer t(s, timed, q, MGB_ST_PROLONG);  // 1331
-        q_prolong(s, q);
+        q_prolong(s, q, s->opt_prolong_mask && s->gs >= 1);
     }
     const bool fuse_post = fuse_sweep && q == s->L - 1;
     {

@@ -943,7 +943,7 @@ struct F8 {
 
 __global__ void __launch_bounds__(256, 2)
 k_prolong_correct8(Geo gc, const double *__restrict__ ec, Geo gf, double *ef, int il_lo,
-                   int il_hi, int chunk)
+                   int il_hi, int chunk, int cmask)
 {
     const int noct = gf.kh >> 2;
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -960,12 +960,18 @@ k_prolong_correct8(Geo gc, const double *__restrict__ ec, Geo gf, double *ef, in
     const int nvalid = min(8, gf.nk - k0);  // fine points k0 .. k0+nvalid-1 exist
     const long long off = (long long)j * gf.kh + 4 * q;
 
+    // cmask bit c: colour c is corrected (the other one is left alone: inside the
+    // V-cycle the post-smoother's first half-sweep overwrites it without reading it)
     auto load_f = [&](int il, F8 &f) {
         const int s = (gf.i0 + il + j) & 1;  // colour holding the even k of this row
         const double *pe = ef + (long long)s * gf.cs + (long long)il * gf.pj + off;
         const double *po = ef + (long long)(s ^ 1) * gf.cs + (long long)il * gf.pj + off;
-        f.e0 = ld2(pe); f.e1 = ld2(pe + 2);
-        f.o0 = ld2(po); f.o1 = ld2(po + 2);
+        if ((cmask >> s) & 1) {
+            f.e0 = ld2(pe); f.e1 = ld2(pe + 2);
+        }
+        if ((cmask >> (s ^ 1)) & 1) {
+            f.o0 = ld2(po); f.o1 = ld2(po + 2);
+        }
     };
     // add the interpolated correction of one fine plane and store it
     auto plane = [&](int il, int oi, const C5 &A0, const C5 &A1, const C5 &B0, const C5 &B1,
@@ -978,6 +984,7 @@ k_prolong_correct8(Geo gc, const double *__restrict__ ec, Geo gf, double *ef, in
                            B0.v[e + 1], B1.v[e], B1.v[e + 1]);
         }
         const int s = (gf.i0 + il + j) & 1;
+        const bool do_e = (cmask >> s) & 1, do_o = (cmask >> (s ^ 1)) & 1;
         double *pe = ef + (long long)s * gf.cs + (long long)il * gf.pj + off;
         double *po = ef + (long long)(s ^ 1) * gf.cs + (long long)il * gf.pj + off;
         const double r0 = __dadd_rn(f.e0.x, ev[0]), r1 = __dadd_rn(f.e0.y, ev[1]);
@@ -985,16 +992,20 @@ k_prolong_correct8(Geo gc, const double *__restrict__ ec, Geo gf, double *ef, in
         const double w0 = __dadd_rn(f.o0.x, od[0]), w1 = __dadd_rn(f.o0.y, od[1]);
         const double w2 = __dadd_rn(f.o1.x, od[2]), w3 = __dadd_rn(f.o1.y, od[3]);
         if (nvalid == 8) {
-            st2(pe, r0, r1); st2(pe + 2, r2, r3);
-            st2(po, w0, w1); st2(po + 2, w2, w3);
+            if (do_e) { st2(pe, r0, r1); st2(pe + 2, r2, r3); }
+            if (do_o) { st2(po, w0, w1); st2(po + 2, w2, w3); }
         } else {  // last octet of the row: even k = k0+2e, odd k = k0+2e+1
-            if (nvalid > 0) pe[0] = r0;
-            if (nvalid > 2) pe[1] = r1;
-            if (nvalid > 4) pe[2] = r2;
-            if (nvalid > 6) pe[3] = r3;
-            if (nvalid > 1) po[0] = w0;
-            if (nvalid > 3) po[1] = w1;
-            if (nvalid > 5) po[2] = w2;
+            if (do_e) {
+                if (nvalid > 0) pe[0] = r0;
+                if (nvalid > 2) pe[1] = r1;
+                if (nvalid > 4) pe[2] = r2;
+                if (nvalid > 6) pe[3] = r3;
+            }
+            if (do_o) {
+                if (nvalid > 1) po[0] = w0;
+                if (nvalid > 3) po[1] = w1;
+                if (nvalid > 5) po[2] = w2;
+            }
         }
     };
 
@@ -1014,9 +1025,7 @@ k_prolong_correct8(Geo gc, const double *__restrict__ ec, Geo gf, double *ef, in
     if (il >= ib)
         return;
     // from here il is even: pairs (il, il+1)
-    F8 Pe, Po, Qe, Qo;
-    Po = F8{};
-    Qe = F8{}; Qo = F8{};
+    F8 Pe = F8{}, Po = F8{}, Qe = F8{}, Qo = F8{};
     load_f(il, Pe);
     if (il + 1 < ib)
         load_f(il + 1, Po);
@@ -1044,12 +1053,81 @@ k_prolong_correct8(Geo gc, const double *__restrict__ ec, Geo gf, double *ef, in
     }
 }
 
-void launch_prolong_correct(const Geo &gc, const double *ec, const Geo &gf,
-                            double *ef, int il_lo, int il_hi, cudaStream_t st)
+// ef[p] = ef[p] + 0. on the face points of one colour (see kernels.h).  Three
+// sections (blockIdx.y): 0 = the two i-faces, whole colour-planes, coalesced;
+// 1 = the rows j = 0 and j = nj-1 of every other plane; 2 = the k = 0 / k = nk-1
+// entries of every remaining row.  Every face point is touched exactly once.
+__global__ void __launch_bounds__(256)
+k_add_zero_faces(Geo g, double *__restrict__ a, int colour, int il_lo, int il_hi)
+{
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    double *base = a + (long long)colour * g.cs;
+    const int lo_face = -g.i0, hi_face = g.ni - 1 - g.i0;  // local indices of the i-faces
+    if (blockIdx.y == 0) {
+        // i-faces inside [il_lo, il_hi): entry t of plane 0 / plane 1
+        const int which = (int)(t / g.pj);
+        if (which > 1)
+            return;
+        const int il = which == 0 ? lo_face : hi_face;
+        if (il < il_lo || il >= il_hi)
+            return;
+        const long long e = t - (long long)which * g.pj;
+        const int j = (int)(e / g.kh), m = (int)(e - (long long)j * g.kh);
+        const int kp = (colour ^ (g.i0 + il + j)) & 1;
+        if (2 * m + kp < g.nk) {
+            double *p = base + (long long)il * g.pj + e;
+            *p = __dadd_rn(*p, 0.);
+        }
+    } else if (blockIdx.y == 1) {
+        // rows j = 0 and j = nj-1 of the planes that are not i-faces
+        const long long per_plane = 2LL * g.kh;
+        const int il = il_lo + (int)(t / per_plane);
+        if (il >= il_hi || il == lo_face || il == hi_face)
+            return;
+        const long long e = t % per_plane;
+        const int j = e < g.kh ? 0 : g.nj - 1;
+        const int m = (int)(e < g.kh ? e : e - g.kh);
+        const int kp = (colour ^ (g.i0 + il + j)) & 1;
+        if (2 * m + kp < g.nk) {
+            double *p = base + (long long)il * g.pj + (long long)j * g.kh + m;
+            *p = __dadd_rn(*p, 0.);
+        }
+    } else {
+        // k = 0 and k = nk-1 of the rows that are on no other face
+        const int il = il_lo + (int)(t / g.nj);
+        const int j = (int)(t % g.nj);
+        if (il >= il_hi || il == lo_face || il == hi_face || j == 0 || j == g.nj - 1)
+            return;
+        const int kp = (colour ^ (g.i0 + il + j)) & 1;
+        double *row = base + (long long)il * g.pj + (long long)j * g.kh;
+        if (kp == 0)
+            row[0] = __dadd_rn(row[0], 0.);  // k = 0
+        if (((g.nk - 1 - kp) & 1) == 0) {    // k = nk-1 has this colour
+            const int m = (g.nk - 1 - kp) >> 1;
+            row[m] = __dadd_rn(row[m], 0.);
+        }
+    }
+}
+
+void launch_add_zero_faces(const Geo &g, double *a, int colour, int il_lo, int il_hi,
+                           cudaStream_t st)
 {
     if (il_hi <= il_lo)
         return;
-    if (launch_tile_prolong(gc, ec, gf, ef, il_lo, il_hi, st))
+    const long long n0 = 2 * g.pj, n1 = (long long)(il_hi - il_lo) * 2 * g.kh,
+                    n2 = (long long)(il_hi - il_lo) * g.nj;
+    const long long most = n0 > n1 ? (n0 > n2 ? n0 : n2) : (n1 > n2 ? n1 : n2);
+    k_add_zero_faces<<<dim3((unsigned)((most + 255) / 256), 3), 256, 0, st>>>(g, a, colour, il_lo,
+                                                                            il_hi);
+    COUNT_LAUNCH();
+}
+
+void launch_prolong_correct(const Geo &gc, const double *ec, const Geo &gf,
+                            double *ef, int il_lo, int il_hi, cudaStream_t st, int cmask)
+{
+    if (il_hi <= il_lo)
+        return;
+    if (launch_tile_prolong(gc, ec, gf, ef, il_lo, il_hi, cmask, st))
         return;
     static const int wide = getenv("MGB_PROLONG_WIDE") ? atoi(getenv("MGB_PROLONG_WIDE")) : 1;
     if (wide) {
@@ -1061,7 +1139,8 @@ void launch_prolong_correct(const Geo &gc, const double *ec, const Geo &gf,
         int chunk = (nplanes + nch - 1) / nch;
         chunk += chunk & 1;  // whole (even, odd) pairs per chunk
         const unsigned by = (unsigned)((nplanes + chunk - 1) / chunk);
-        k_prolong_correct8<<<dim3(bx, by), 256, 0, st>>>(gc, ec, gf, ef, il_lo, il_hi, chunk);
+        k_prolong_correct8<<<dim3(bx, by), 256, 0, st>>>(gc, ec, gf, ef, il_lo, il_hi, chunk,
+                                                         cmask);
         COUNT_LAUNCH();
         return;
     }

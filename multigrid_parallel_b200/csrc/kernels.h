@@ -43,8 +43,14 @@ void launch_residual_restrict(const Geo &gf, const double *vf, const double *df,
 
 // trilinear prolongation + correction (mg_3d.h:1000-1145) for local fine
 // planes [il_lo, il_hi)
+// cmask: bit c set = colour c is corrected (3 = the reference's operation; inside the
+// V-cycle only the colour the post-smoother does not overwrite first is needed)
 void launch_prolong_correct(const Geo &gc, const double *ec, const Geo &gf,
-                            double *ef, int il_lo, int il_hi, cudaStream_t st);
+                            double *ef, int il_lo, int il_hi, cudaStream_t st, int cmask = 3);
+// a[p] = a[p] + 0. on the face points of colour `colour` in local planes [il_lo, il_hi):
+// what the reference's `ef[p] += 0.` does to a boundary value (-0. becomes +0.)
+void launch_add_zero_faces(const Geo &g, double *a, int colour, int il_lo, int il_hi,
+                           cudaStream_t st);
 
 // sum of squares of the entries of one or two ranges (pads are zero) -> *out
 void launch_sumsq(const double *a0, long long n0, const double *a1, long long n1,
@@ -116,7 +122,7 @@ void tile_plan_query(int kind, const Geo &gf, const Geo *gc, int p_lo, int p_hi,
 // prolongation + correction through the TMA ring (tile.cu); false: use launch_prolong_correct's
 // marching kernels
 bool launch_tile_prolong(const Geo &gc, const double *ec, const Geo &gf, double *ef, int il_lo,
-                         int il_hi, cudaStream_t st);
+                         int il_hi, int cmask, cudaStream_t st);
 
 // dense coarse operator + LU (mg_3d.h:147-273, gauss_elim.h:9-60)
 void launch_coarse_matrix(double *A, int ni, int nj, int nk, double h,

@@ -191,6 +191,7 @@ struct TileP {
     int TY;            // RESTRICT: coarse rows per tile
     int p_lo, p_hi;    // NORM: fine local planes [p_lo,p_hi); RESTRICT: coarse local planes
     int chunk;         // planes per blockIdx.z
+    int cmask;         // prolongation: bit c set = colour c is corrected (3: both)
 };
 
 // SWEEP = -1: no fused sweep; 0/1: colour swept one plane ahead of the residual
@@ -858,7 +859,13 @@ k_tile_prolong(const TileP P, const double *__restrict__ ec,
     const Geo &g = P.gf, &gc = P.gc;
     const int TRt = TRT > 0 ? TRT : P.TRt, TQt = TQT > 0 ? TQT : P.TQt;
     const int RS = TRt + 2, PW = 2 * (TQt + 2);
-    const int slot_d = (2 * RS * PW + 15) & ~15;
+    // cmask == 3: both colours travel through the ring; otherwise only the one
+    // colour that is corrected (the other one is about to be overwritten by the
+    // post-smoother's first half-sweep, which does not read it)
+    const bool both = P.cmask == 3;
+    const int only = P.cmask == 2 ? 1 : 0;  // the single colour, if !both
+    const int ncol = both ? 2 : 1;
+    const int slot_d = (ncol * RS * PW + 15) & ~15;
     const int col1 = RS * PW;
     uint64_t *bars = reinterpret_cast<uint64_t *>(tile_smem);
     double *ring = reinterpret_cast<double *>(tile_smem + 128);
@@ -876,7 +883,7 @@ k_tile_prolong(const TileP P, const double *__restrict__ ec,
         return;
     const int pr0 = ia, plast = ib - 1;
     const uint32_t ring_u32 = smem_u32(ring), bars_u32 = smem_u32(bars);
-    const uint32_t box_bytes = (uint32_t)(2 * RS * PW) * 8u, slot_bytes = (uint32_t)slot_d * 8u;
+    const uint32_t box_bytes = (uint32_t)(ncol * RS * PW) * 8u, slot_bytes = (uint32_t)slot_d * 8u;
     const int c0 = 2 * (mq0 - 1), c1 = jt0 - 1;
     if (tid == 0) {
         for (int s = 0; s < S; s++)
@@ -891,7 +898,7 @@ k_tile_prolong(const TileP P, const double *__restrict__ ec,
         while (iss_p <= plast && iss_p - S <= dead) {
             const uint32_t bar = bars_u32 + 8 * iss_s;
             mbar_arrive_expect_tx(bar, box_bytes);
-            tma_load_4d(ring_u32 + iss_s * slot_bytes, &tm_v, c0, c1, iss_p, 0, bar);
+            tma_load_4d(ring_u32 + iss_s * slot_bytes, &tm_v, c0, c1, iss_p, both ? 0 : only, bar);
             iss_p++;
             iss_s = iss_s + 1 == S ? 0 : iss_s + 1;
         }
@@ -924,20 +931,27 @@ k_tile_prolong(const TileP P, const double *__restrict__ ec,
         const double *q = ring + c_s * slot_d + so;
         if (work) {
             const int s = (g.i0 + t + j) & 1;  // colour holding the even k of this row
-            const double2 fe = ld2(q + (s ? col1 : 0)), fo = ld2(q + (s ? 0 : col1));
-            const double e0 = t_pc_even(oi, oj, A0.x, A1.x, B0.x, B1.x);
-            const double e1 = t_pc_even(oi, oj, A0.y, A1.y, B0.y, B1.y);
-            const double o0 = t_pc_odd(oi, oj, A0.x, A0.y, A1.x, A1.y, B0.x, B0.y, B1.x, B1.y);
-            const double o1 = t_pc_odd(oi, oj, A0.y, A0.z, A1.y, A1.z, B0.y, B0.z, B1.y, B1.z);
-            double *pe = pf + (s ? g.cs : 0), *po = pf + (s ? 0 : g.cs);
-            if (v2)
-                st2(pe, __dadd_rn(fe.x, e0), __dadd_rn(fe.y, e1));
-            else
-                pe[0] = __dadd_rn(fe.x, e0);
-            if (v3)
-                st2(po, __dadd_rn(fo.x, o0), __dadd_rn(fo.y, o1));
-            else if (v1)
-                po[0] = __dadd_rn(fo.x, o0);
+            const bool do_e = both || only == s, do_o = both || only != s;
+            if (do_e) {
+                const double2 fe = ld2(q + (both && s ? col1 : 0));
+                const double e0 = t_pc_even(oi, oj, A0.x, A1.x, B0.x, B1.x);
+                const double e1 = t_pc_even(oi, oj, A0.y, A1.y, B0.y, B1.y);
+                double *pe = pf + (s ? g.cs : 0);
+                if (v2)
+                    st2(pe, __dadd_rn(fe.x, e0), __dadd_rn(fe.y, e1));
+                else
+                    pe[0] = __dadd_rn(fe.x, e0);
+            }
+            if (do_o) {
+                const double2 fo = ld2(q + (both && !s ? col1 : 0));
+                const double o0 = t_pc_odd(oi, oj, A0.x, A0.y, A1.x, A1.y, B0.x, B0.y, B1.x, B1.y);
+                const double o1 = t_pc_odd(oi, oj, A0.y, A0.z, A1.y, A1.z, B0.y, B0.z, B1.y, B1.z);
+                double *po = pf + (s ? 0 : g.cs);
+                if (v3)
+                    st2(po, __dadd_rn(fo.x, o0), __dadd_rn(fo.y, o1));
+                else if (v1)
+                    po[0] = __dadd_rn(fo.x, o0);
+            }
         }
         c_s = c_s + 1 == S ? 0 : c_s + 1;
         pf += g.pj;
@@ -949,6 +963,152 @@ k_tile_prolong(const TileP P, const double *__restrict__ ec,
         if (work && has_odd) {  // coarse plane I+1: requested now, used by the odd plane
             B0 = t_ld_c3(gc, ec, I + 1, J0, mq);
             B1 = oj ? t_ld_c3(gc, ec, I + 1, J0 + 1, mq) : B0;
+        }
+        plane(t, 0);
+        if (has_odd) {
+            plane(t + 1, 1);
+            A0 = B0;
+            A1 = B1;
+            I++;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// The same for ONE colour (inside the V-cycle only the colour the post-smoother
+// does not overwrite first needs the correction: 9 instead of 17 B/DOF).  A
+// thread owns two quads (k = 8o .. 8o+7), i.e. the two pairs of that colour, so
+// that it still has four points per plane; ring = that colour only.
+// ---------------------------------------------------------------------------
+struct TC5 {
+    double v[5];  // coarse entries K = 4o .. 4o+4
+};
+__device__ __forceinline__ TC5 t_ld_c5(const Geo &gc, const double *__restrict__ ec, int Il, int J,
+                                       int o)
+{
+    const int S = (gc.i0 + Il + J) & 1;  // colour of the even K in this coarse row
+    const long long row = ((long long)Il * gc.nj + J) * gc.kh + 2 * o;
+    const double *e0 = ec + (long long)S * gc.cs + row;
+    const double *e1 = ec + (long long)(S ^ 1) * gc.cs + row;
+    const double2 a = ld2(e0), b = ld2(e1);
+    TC5 r;
+    r.v[0] = a.x; r.v[1] = b.x; r.v[2] = a.y; r.v[3] = b.y;
+    r.v[4] = e0[2];
+    return r;
+}
+
+template <int COLOUR>
+__global__ void __launch_bounds__(384, 2)
+k_tile_prolong_one(const TileP P, const double *__restrict__ ec,
+                   const __grid_constant__ CUtensorMap tm_v)
+{
+    constexpr int S = 4;
+    extern __shared__ __align__(128) unsigned char tile_smem[];
+    const Geo &g = P.gf, &gc = P.gc;
+    const int TRt = P.TRt, TQt = P.TQt;  // TQt quads (even) = TQt/2 octets per row
+    const int TOt = TQt >> 1;
+    const int RS = TRt + 2, PW = 2 * (TQt + 2);
+    const int slot_d = (RS * PW + 15) & ~15;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(tile_smem);
+    double *ring = reinterpret_cast<double *>(tile_smem + 128);
+    const int tid = threadIdx.x;
+    const int jl = tid / TOt, ol = tid - jl * TOt;
+    const int jt0 = blockIdx.y * P.TRo, mq0 = blockIdx.x * P.TQo;
+    const int j = jt0 + jl, mq = mq0 + 2 * ol;  // first of the thread's two quads
+    const int o = mq >> 1;                      // its octet (mq0 is even)
+    const int k0 = 4 * mq;
+    const bool work = jl < TRt && j < g.nj && k0 < g.nk;
+    const int ia = P.p_lo + blockIdx.z * P.chunk;  // even global plane
+    const int ib = min(ia + P.chunk, P.p_hi);
+    if (ia >= ib)
+        return;
+    const int pr0 = ia, plast = ib - 1;
+    const uint32_t ring_u32 = smem_u32(ring), bars_u32 = smem_u32(bars);
+    const uint32_t box_bytes = (uint32_t)(RS * PW) * 8u, slot_bytes = (uint32_t)slot_d * 8u;
+    const int c0 = 2 * (mq0 - 1), c1 = jt0 - 1;
+    if (tid == 0) {
+        for (int s = 0; s < S; s++)
+            mbar_init(bars_u32 + 8 * s, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    int iss_p = pr0, iss_s = 0;
+    auto issue_upto = [&](int dead) {
+        if (tid != 0)
+            return;
+        while (iss_p <= plast && iss_p - S <= dead) {
+            const uint32_t bar = bars_u32 + 8 * iss_s;
+            mbar_arrive_expect_tx(bar, box_bytes);
+            tma_load_4d(ring_u32 + iss_s * slot_bytes, &tm_v, c0, c1, iss_p, COLOUR, bar);
+            iss_p++;
+            iss_s = iss_s + 1 == S ? 0 : iss_s + 1;
+        }
+    };
+    int w_s = 0;
+    uint32_t w_par = 0;
+    auto wait_next = [&]() {
+        mbar_wait(bars_u32 + 8 * w_s, w_par);
+        if (++w_s == S) {
+            w_s = 0;
+            w_par ^= 1;
+        }
+    };
+    issue_upto(pr0 - 1);
+
+    const long long offq = (long long)j * g.kh + 2 * mq;
+    const int so = (jl + 1) * PW + 2 * (2 * ol + 1);
+    const int oj = j & 1, J0 = j >> 1;
+    int I = ((g.i0 + ia) >> 1) - gc.i0;  // coarse plane under fine plane ia
+    TC5 A0{}, A1{}, B0{}, B1{};
+    if (work) {
+        A0 = t_ld_c5(gc, ec, I, J0, o);
+        A1 = oj ? t_ld_c5(gc, ec, I, J0 + 1, o) : A0;
+    }
+    B0 = A0;
+    B1 = A1;
+    int c_s = 0;
+    double *pf = P.vw + (long long)COLOUR * g.cs + (long long)ia * g.pj + offq;
+    auto plane = [&](int t, int oi) {
+        wait_next();  // plane t
+        const double *q = ring + c_s * slot_d + so;
+        if (work) {
+            const int s = (g.i0 + t + j) & 1;  // colour holding the even k of this row
+            const double2 f0 = ld2(q), f1 = ld2(q + 2);  // quad mq, quad mq+1
+            double r[4];
+            int kk;  // k of the first of the four points; they are 2 apart
+            if (COLOUR == s) {  // this colour holds the even k: 8o, 8o+2, 8o+4, 8o+6
+                kk = k0;
+#pragma unroll
+                for (int e = 0; e < 4; e++)
+                    r[e] = t_pc_even(oi, oj, A0.v[e], A1.v[e], B0.v[e], B1.v[e]);
+            } else {            // ... the odd k: 8o+1 .. 8o+7
+                kk = k0 + 1;
+#pragma unroll
+                for (int e = 0; e < 4; e++)
+                    r[e] = t_pc_odd(oi, oj, A0.v[e], A0.v[e + 1], A1.v[e], A1.v[e + 1], B0.v[e],
+                                    B0.v[e + 1], B1.v[e], B1.v[e + 1]);
+            }
+            const double w0 = __dadd_rn(f0.x, r[0]), w1 = __dadd_rn(f0.y, r[1]);
+            const double w2 = __dadd_rn(f1.x, r[2]), w3 = __dadd_rn(f1.y, r[3]);
+            if (kk + 6 < g.nk) {
+                st2(pf, w0, w1);
+                st2(pf + 2, w2, w3);
+            } else {  // end of the row
+                if (kk < g.nk) pf[0] = w0;
+                if (kk + 2 < g.nk) pf[1] = w1;
+                if (kk + 4 < g.nk) pf[2] = w2;
+            }
+        }
+        c_s = c_s + 1 == S ? 0 : c_s + 1;
+        pf += g.pj;
+        __syncthreads();
+        issue_upto(t);
+    };
+    for (int t = ia; t < ib; t += 2) {
+        const bool has_odd = t + 1 < ib;
+        if (work && has_odd) {  // coarse plane I+1: requested now, used by the odd plane
+            B0 = t_ld_c5(gc, ec, I + 1, J0, o);
+            B1 = oj ? t_ld_c5(gc, ec, I + 1, J0 + 1, o) : B0;
         }
         plane(t, 0);
         if (has_odd) {
@@ -1180,12 +1340,14 @@ bool launch_cfg(const TileCfg &c, cudaStream_t st)
 // (no halo threads), 4 ring slots of `ncol` colours; `pairs`: chunks hold whole
 // (even, odd) plane pairs
 static bool plan_simple(TileCfg &c, const Geo &g, int il_lo, int il_hi, int rows, int qcap,
-                        int ncol, bool pairs)
+                        int ncol, bool pairs, bool octets = false)
 {
     TileP &p = c.p;
     p.gf = g;
     const int nq = (g.nk + 3) / 4;
     p.TQo = p.TQt = even_tile(nq, qcap);
+    if (octets && (p.TQt & 1))  // a thread owns two quads: even tile widths
+        p.TQo = p.TQt = p.TQt + 1;
     p.TRo = p.TRt = even_tile(g.nj, rows);
     p.TY = 0;
     c.grid.x = (nq + p.TQo - 1) / p.TQo;
@@ -1199,7 +1361,7 @@ static bool plan_simple(TileCfg &c, const Geo &g, int il_lo, int il_hi, int rows
     c.grid.z = (nplanes + p.chunk - 1) / p.chunk;
     p.p_lo = il_lo;
     p.p_hi = il_hi;
-    c.threads = ((p.TRt * p.TQt + 31) / 32) * 32;
+    c.threads = ((p.TRt * (octets ? p.TQt / 2 : p.TQt) + 31) / 32) * 32;
     const size_t RS = p.TRt + 2, PW = 2 * (p.TQt + 2);
     const size_t slot_d = ((size_t)ncol * RS * PW + 15) & ~(size_t)15;
     c.smem = 128 + 4 * slot_d * 8;
@@ -1329,7 +1491,7 @@ bool launch_tile_half_sweep(const Geo &g, double *v, const double *d, double hSq
 
 // prolongation + correction of local fine planes [il_lo, il_hi) through the TMA ring
 bool launch_tile_prolong(const Geo &gc, const double *ec, const Geo &gf, double *ef, int il_lo,
-                         int il_hi, cudaStream_t st)
+                         int il_hi, int cmask, cudaStream_t st)
 {
     static const int on = env_int("MGB_TILE_PROLONG", 1);
     static const long long min_plane = env_int("MGB_TILE_PROLONG_MIN_PLANE", 200000);
@@ -1337,15 +1499,43 @@ bool launch_tile_prolong(const Geo &gc, const double *ec, const Geo &gf, double 
         ((long long)gf.nj * gf.nk < min_plane && g_tile_min_plane > 0) || ((gf.i0 + il_lo) & 1))
         return false;
     TileCfg c{};
+    if (cmask != 3) {
+        // one colour: threads own octets (two quads), tiles of an even number of quads
+        static const int rows1 = env_int("MGB_TILE_PROLONG1_R", 8),
+                         qcap1 = env_int("MGB_TILE_PROLONG1_Q", 44) & ~1;
+        if (!plan_simple(c, gf, il_lo, il_hi, rows1, qcap1, 1, true, true))
+            return false;
+        TileP &p = c.p;
+        const size_t RS = p.TRt + 2, PW = 2 * (p.TQt + 2);
+        p.gc = gc;
+        p.cmask = cmask;
+        p.v = ef; p.vw = ef; p.d = nullptr; p.hSq = 0.; p.invHsq = 0.;
+        CUtensorMap tm1;
+        if (!make_tensor_map(&tm1, gf, ef, (int)PW, (int)RS, 1))
+            return false;
+        static bool attr1 = false;
+        if (!attr1) {
+            cudaFuncSetAttribute(k_tile_prolong_one<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024);
+            cudaFuncSetAttribute(k_tile_prolong_one<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024);
+            attr1 = true;
+        }
+        if (cmask == 2)
+            k_tile_prolong_one<1><<<c.grid, c.threads, c.smem, st>>>(c.p, ec, tm1);
+        else
+            k_tile_prolong_one<0><<<c.grid, c.threads, c.smem, st>>>(c.p, ec, tm1);
+        ++*launch_counter();
+        return true;
+    }
     if (!plan_simple(c, gf, il_lo, il_hi, env_int("MGB_TILE_PROLONG_R", 6),
                      env_int("MGB_TILE_PROLONG_Q", 43), 2, true))
         return false;
     TileP &p = c.p;
     p.gc = gc;
+    p.cmask = cmask;
     const size_t RS = p.TRt + 2, PW = 2 * (p.TQt + 2);
     p.v = ef; p.vw = ef; p.d = nullptr; p.hSq = 0.; p.invHsq = 0.;
     CUtensorMap tm_v;
-    if (!make_tensor_map(&tm_v, gf, ef, (int)PW, (int)RS, 2))
+    if (!make_tensor_map(&tm_v, gf, ef, (int)PW, (int)RS, cmask == 3 ? 2 : 1))
         return false;
     static bool attr = false;
     if (!attr) {

@@ -12,6 +12,7 @@ from ._lib import c_dp, check, load_library
 
 MGB_U, MGB_D, MGB_R = 0, 1, 2
 OPT_GRAPH, OPT_PROFILE, OPT_FUSE, OPT_GRAPH_LEVELS, OPT_TAIL, OPT_ZERO_GUESS = 0, 1, 2, 3, 4, 5
+OPT_PROLONG_MASK = 6
 # mg_3d.h:136-137
 STAGE_NAMES = ("Smoother1", "CalcResidual1", "Restrict Residual", "Recurse, Direct Solve",
                "Prolongate&Correct", "Smoother2", "CalcResidual2")

@@ -284,7 +284,7 @@ def test_stateless_transfer_operators(mgb, orc):
 
 
 @pytest.mark.parametrize("coarse,levels,gs", [((3, 3, 3), 5, 2), ((5, 5, 5), 3, 1), ((3, 5, 9), 4, 3)])
-@pytest.mark.parametrize("mode", ["graph", "eager", "profile", "unfused", "fuse1", "fuse2", "notail", "nozeroguess"])
+@pytest.mark.parametrize("mode", ["graph", "eager", "profile", "unfused", "fuse1", "fuse2", "notail", "nozeroguess", "noprolongmask"])
 def test_vcycle_bitwise_all_levels(mgb, orc, coarse, levels, gs, mode):
     """one and several V-cycles: every level's u and d match the oracle bit
     for bit, the returned norm to 1e-13"""
@@ -306,6 +306,8 @@ def test_vcycle_bitwise_all_levels(mgb, orc, coarse, levels, gs, mode):
             s.set_option(OPT_TAIL, 0)
         elif mode == "nozeroguess":
             s.set_option(OPT_ZERO_GUESS, 0)
+        elif mode == "noprolongmask":
+            s.set_option(6, 0)
         top = levels - 1
         u0, d0 = seeded(s.dims(top), 41), seeded(s.dims(top), 42)
         mg.u(top)[...] = u0
@@ -354,4 +356,30 @@ def test_vcycle_after_coarse_levels_were_overwritten(mgb, orc, graph):
             assert got == pytest.approx(want, rel=NORM_RTOL), cyc
             for lvl in range(levels):
                 assert np.array_equal(s.download(lvl, mgb.MGB_U), mg.u(lvl)), (cyc, lvl)
+        mg.close()
+
+
+def test_vcycle_keeps_the_sign_of_zero_on_the_faces(mgb, orc):
+    """the reference's prolongation does `ef[p] += 0.` on every face point, which
+    turns a -0. boundary value into +0.; the colour-masked prolongation of the
+    cycle must do the same (np.array_equal cannot see the difference: signbit)"""
+    coarse, levels, gs = (3, 3, 3), 5, 2
+    mg = OrcMG(orc, coarse, levels, gs)
+    with _mk(mgb, coarse, levels, gs) as s:
+        top = levels - 1
+        u0, d0 = seeded(s.dims(top), 91), seeded(s.dims(top), 92)
+        for a in (u0,):
+            a[0, :, :] = -0.0; a[-1, :, :] = -0.0
+            a[:, 0, :] = -0.0; a[:, -1, :] = -0.0
+            a[:, :, 0] = -0.0; a[:, :, -1] = -0.0
+        mg.u(top)[...] = u0
+        mg.d(top)[...] = d0
+        s.upload(top, mgb.MGB_U, u0)
+        s.upload(top, mgb.MGB_D, d0)
+        for cyc in range(2):
+            mg.vcycle()
+            s.vcycle()
+            got, want = s.download(top, mgb.MGB_U), mg.u(top)
+            assert np.array_equal(got, want)
+            assert np.array_equal(np.signbit(got), np.signbit(want)), cyc
         mg.close()
