@@ -36,7 +36,10 @@ HALF_SWEEP_BYTES_PER_DOF = 12.0       # read 1/2 v, read 1/2 d, wri
 # SURVEY 8(d) algorithmic bytes per DOF of the other finest-level stages
 # stage -> (kernel as named in profiles/traffic.json, what it is, bytes per DOF)
 STAGE_BYTES_PER_DOF = {"CalcResidual1": ("k_tile<-1,1,2,11,34>", "residual+restrict (TMA tile kernel)", 17.0),
-                       "Prolongate&Correct": ("k_tile_prolong<6,43>", "prolongation+correction (TMA ring)", 17.0),
+                       # inside the cycle only the red points are corrected (the post-smoother's
+                       # first half-sweep overwrites the black ones): 1 + 4 + 4 B/DOF
+                       "Prolongate&Correct": ("k_tile_prolong_one<1>", "prolongation+correction of the red "
+                                              "points (TMA ring) + face fix-up kernel", 9.0),
                        "CalcResidual2": ("k_tile<-1,0,2,5,43>", "residual norm (TMA tile kernel)", 16.0)}
 
 
