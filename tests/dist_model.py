@@ -49,7 +49,12 @@ class SlabLevel:
 class SlabMG:
     """mirror of mgb_create_dist + enqueue_cycle for one rank"""
 
-    def __init__(self, lib, orc, coarse, levels, gs, rank, world, min_planes=2, min_points=0):
+    def __init__(self, lib, orc, coarse, levels, gs, rank, world, min_planes=2, min_points=0,
+                 shortcuts=False):
+        # shortcuts: the two exact short-cuts libmgb's cycle takes -- coarse levels are
+        # not zeroed (first RED half-sweep with the guess taken as 0), the
+        # prolongation corrects RED points only (api.cu: enqueue_cycle, q_prolong)
+        self.shortcuts = shortcuts and gs >= 1
         self.lib, self.orc, self.rank, self.world, self.gs = lib, orc, rank, world, gs
         self.L = levels
         self.LD = lib.mgb_plan_first_dist_level(*coarse, levels, world, min_planes, min_points)
@@ -108,9 +113,36 @@ class SlabMG:
         if lv.dist:
             self._xchg(lv.u, lv, lv.own_hi - 1, lv.own_lo - 1, lv.own_lo, lv.own_hi)
 
-    def smooth(self, q, first_red):
-        for _ in range(self.gs):
-            self.half_sweep(q, 1 if first_red else 0)
+    def _colour_mask(self, lv, lo, hi, colour):
+        """points of global colour `colour` on local planes [lo, hi) (global indices)"""
+        i, j, k = np.meshgrid(np.arange(lo, hi), np.arange(lv.nj), np.arange(lv.nk), indexing="ij")
+        return ((i + j + k) & 1) == colour
+
+    def first_sweep_zero(self, q, colour):
+        """k_first_sweep_zero: the update with all six neighbours 0, owned interior
+        planes only, nothing of the old array is read"""
+        if not self.works_on(q):
+            return
+        lv = self.lv[q]
+        lo, hi = lv.sweep
+        if hi > lo:
+            s = np.zeros((hi - lo, lv.nj, lv.nk))
+            for _ in range(5):
+                s = s + 0.0
+            new = (1.0 / 6) * (s - (lv.h * lv.h) * lv.d[lv.loc(lo):lv.loc(hi)])
+            sel = self._colour_mask(lv, lo, hi, colour)
+            sel[:, 0, :] = sel[:, -1, :] = False
+            sel[:, :, 0] = sel[:, :, -1] = False
+            lv.u[lv.loc(lo):lv.loc(hi)][sel] = new[sel]
+        if lv.dist:
+            self._xchg(lv.u, lv, lv.own_hi - 1, lv.own_lo - 1, lv.own_lo, lv.own_hi)
+
+    def smooth(self, q, first_red, zero_guess=False):
+        for it in range(self.gs):
+            if zero_guess and it == 0:
+                self.first_sweep_zero(q, 1 if first_red else 0)
+            else:
+                self.half_sweep(q, 1 if first_red else 0)
             self.half_sweep(q, 0 if first_red else 1)
 
     def residual_sumsq(self, q):
@@ -160,6 +192,33 @@ class SlabMG:
     def prolong(self, q):
         if not self.works_on(q):
             return
+        f = self.lv[q]
+        if not self.shortcuts:
+            self._prolong_full(q)
+            return
+        # red-only: run the reference's operation on a copy, keep its RED points on the
+        # planes the rank updates; black face points of the finest level get `+ 0.`
+        lo = f.own_lo - (1 if (f.dist and self.rank > 0) else 0)
+        hi = f.own_hi + (1 if (f.dist and self.rank < self.world - 1) else 0)
+        before = f.u.copy()
+        self._prolong_full(q)
+        after = f.u.copy()
+        f.u[...] = before
+        red = self._colour_mask(f, lo, hi, 1)
+        f.u[f.loc(lo):f.loc(hi)][red] = after[f.loc(lo):f.loc(hi)][red]
+        if q == self.L - 1:
+            a, b = f.own_lo, f.own_hi
+            face = np.zeros((b - a, f.nj, f.nk), bool)
+            face[:, 0, :] = face[:, -1, :] = True
+            face[:, :, 0] = face[:, :, -1] = True
+            for I in (0, f.ni - 1):
+                if a <= I < b:
+                    face[I - a] = True
+            sel = face & self._colour_mask(f, a, b, 0)
+            blk = f.u[f.loc(a):f.loc(b)]
+            blk[sel] = blk[sel] + 0.0
+
+    def _prolong_full(self, q):
         f, c = self.lv[q], self.lv[q - 1]
         if not f.dist:
             self.orc.prolong_correct(c.u, f.u)
@@ -187,12 +246,13 @@ class SlabMG:
         if not self.works_on(q):
             return
         lv = self.lv[q]
-        if q < self.L - 1:
+        zero_guess = self.shortcuts and 0 < q < self.L - 1
+        if q < self.L - 1 and not zero_guess:
             lv.u[...] = 0.0
         if q == 0:
             lv.u[...] = self.orc.lu_solve(self.lu, lv.d.reshape(-1)).reshape(lv.u.shape)
             return
-        self.smooth(q, True)
+        self.smooth(q, True, zero_guess)
         self.residual_restrict(q)
         self.cycle_level(q - 1)
         if q == self.LD:
