@@ -12,53 +12,89 @@ download).  `roofline` is the RB-GS half-sweep kernel (12 B/DOF algorithmic)
 against the measured HBM copy peak; `cpu_baseline` is the reference itself
 (oracle/_ref, built from /root/reference) on this box's host cores.
 
---impl reference times the reference's own OpenMP implementation on the host.
+The line also carries the other BASELINE configs as objects: `rbgs` (config 2:
+RB-GS sweeps alone at 257^3 / 513^3), `strong1025` (config 4), `config5` (1025 x
+1025 x (256N+1) with the dense-LU coarse grid 9 x 9 x (2N+1)), and for N > 1
+`parity`: the partitioned solver against the single-GPU one, bit for bit, checked
+BEFORE anything is timed -- the run fails (rc 1) if it is not bitwise.
+
+--impl reference times the reference's own OpenMP implementation on the host
+(all host cores, in a fresh process so libgomp sees the thread settings).
 Nothing here reads /root/reference at run time.
 """
-import argparse
-import json
-import math
 import os
-import subprocess
-import sys
-import threading
-import time
+
+# Read BEFORE anything can load libgomp: with OMP_PROC_BIND set, libgomp pins the
+# main thread to one place when it is loaded, after which the affinity mask says
+# "1 CPU" (that is how round 1's reference arm came to run on one thread).
+
+
+def _host_cpu_set():
+    try:
+        cpus = set(os.sched_getaffinity(0))
+    except AttributeError:  # pragma: no cover
+        return set(range(os.cpu_count() or 1))
+    if len(cpus) > 1 or not os.environ.get("OMP_PROC_BIND"):
+        return cpus
+    # one CPU AND binding requested: a libgomp loaded earlier (by an import before this
+    # module, or by the launcher we inherited the mask from) has most likely pinned this
+    # thread.  Ask the processes that were not pinned, and the cgroup.
+    for pid in (os.getppid(), 1):
+        try:
+            other = set(os.sched_getaffinity(pid))
+            if len(other) > len(cpus):
+                cpus = other
+        except OSError:
+            pass
+    if len(cpus) == 1:
+        try:
+            txt = open("/sys/fs/cgroup/cpuset.cpus.effective").read().strip()
+            eff = set()
+            for p in txt.split(","):
+                if "-" in p:
+                    eff.update(range(int(p.split("-")[0]), int(p.split("-")[1]) + 1))
+                elif p:
+                    eff.add(int(p))
+            if len(eff) > 1:
+                cpus = eff
+        except (OSError, ValueError):
+            pass
+    return cpus
+
+
+HOST_CPU_SET = _host_cpu_set()
+HOST_CPUS = len(HOST_CPU_SET)
+
+import argparse  # noqa: E402
+import json  # noqa: E402
+import subprocess  # noqa: E402
+import sys  # noqa: E402
+import threading  # noqa: E402
+import time  # noqa: E402
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 COARSE, LEVELS, GS = 3, 9, 2          # test_mg_3d 3 9 2 -> 513^3
-TOL = 1e-8                            # test_mg_3d.c:19
 METRIC = "vcycle_dof_per_s"
 UNIT = "DOF*cycles/s"
-HALF_SWEEP_BYTES_PER_DOF = 12.0       # SURVEY 8(d): read 1/2 v, read 1/2 d, write 1/2 v
-# SURVEY 8(d) algorithmic bytes per DOF of the other finest-level stages
-# stage -> (kernel as named in profiles/traffic.json, what it is, bytes per DOF)
-STAGE_BYTES_PER_DOF = {"CalcResidual1": ("k_tile<-1,1,2,11,34>", "residual+restrict (TMA tile kernel)", 17.0),
-                       # inside the cycle only the red points are corrected (the post-smoother's
-                       # first half-sweep overwrites the black ones): 1 + 4 + 4 B/DOF
-                       "Prolongate&Correct": ("k_tile_prolong_one<1>", "prolongation+correction of the red "
-                                              "points (TMA ring) + face fix-up kernel", 9.0),
-                       "CalcResidual2": ("k_tile<-1,0,2,5,43>", "residual norm (TMA tile kernel)", 16.0)}
 
 
-def ncu_traffic(kernel):
-    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` from the
-    committed `ncu --set full` summary (profiles/traffic.json), or None"""
-    try:
-        t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-        return t[kernel]["dram_bytes_per_launch"]
-    except Exception:
-        return None
-
-
-def measured_peak_gbs():
-    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    try:
-        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
-    except Exception:
-        return 6650.0, "fallback (B200_PROFILING.md)"
+def workload_config(n_gpus):
+    """`config` of the JSON line -- the SAME dict in both arms (ours / --impl reference)"""
+    if n_gpus == 1:
+        return {"workload": f"test_mg_3d {COARSE} {LEVELS} {GS}: 513^3 fp64 Laplace V(2,2)-cycle, "
+                            "Dirichlet x^2-2y^2+z^2, coarse 3^3 LU, stopping rule 1e-8*||d||",
+                "parallelism": "single GPU",
+                "l2": "inputs larger than L2 (3 x 1.1 GB level arrays vs 126 MB)"}
+    return {"workload": f"{512 * n_gpus + 1}x513x513 fp64 Laplace V(2,2)-cycle (the 513^3 problem of "
+                        f"test_mg_3d 3 9 2 stretched along i: 512 planes of 513^2 per GPU), Dirichlet "
+                        f"x^2-2y^2+z^2, coarse {2 * n_gpus + 1}x3x3 LU, {LEVELS} levels, stopping rule "
+                        "1e-8*||d||",
+            "parallelism": f"i-slabs over {n_gpus} GPUs (one process per GPU), halo planes over NVLink "
+                           "peer memory, coarse levels below the partitioning threshold on one GPU",
+            "l2": "inputs larger than L2 (3 x 1.1 GB level arrays per GPU vs 126 MB)"}
 
 
 class ClockSampler(threading.Thread):
@@ -128,62 +164,99 @@ class ClockSampler(threading.Thread):
 # --------------------------------------------------------------------------
 # reference arm / CPU baseline: the reference's own OpenMP code on host cores
 # --------------------------------------------------------------------------
-def cpu_reference_cycles(coarse, levels, gs, warm, timed):
-    """`warm`+`timed` V-cycles of the reference (oracle/_ref/libmg_ref.so);
-    returns (seconds for the timed cycles, threads, N)"""
+def cpu_worker(argv):
+    """child process: `warm` + `timed` V-cycles of the reference (oracle/_ref/libmg_ref.so,
+    the unmodified mg_3d.h behind oracle/ref_harness.c), the timed ones inside the
+    driver's own timed region (test_mg_3d.c:36-68: one parallel region around the loop,
+    omp_get_wtime on both sides).  Thread count and binding come from the environment the
+    parent set BEFORE this process started."""
     import ctypes as C
 
     from oracle_lib import Ref, c_dp
+    coarse, levels, gs, warm, timed, want_threads = [int(x) for x in argv]
     ref = Ref()
     if not ref.available:
-        raise RuntimeError("oracle/_ref/libmg_ref.so missing (built by __graft_entry__.build() "
-                           "where /root/reference exists)")
+        print(json.dumps({"error": "oracle/_ref/libmg_ref.so missing (built by __graft_entry__."
+                                   "build() where /root/reference exists)"}))
+        return 0
     L = ref.L
-    # all the host threads this process may use (torchrun exports OMP_NUM_THREADS=1,
-    # which would silently turn the OpenMP reference into a serial run)
-    try:
-        ncores = len(os.sched_getaffinity(0))
-    except AttributeError:
-        ncores = os.cpu_count() or 1
-    ref.set_threads(ncores)
+    L.ref_timed_cycles.restype = C.c_double
+    L.ref_timed_cycles.argtypes = [C.c_int, c_dp]
+    threads = L.ref_max_threads()
+    if threads != want_threads:
+        print(json.dumps({"error": f"OpenMP offers {threads} threads, wanted {want_threads}"}))
+        return 0
     grid, rhs, h = c_dp(), c_dp(), C.c_double()
     N = L.ref_solver_open(coarse, levels, gs, C.byref(grid), C.byref(rhs), C.byref(h))
     # test_mg_3d.c:17-29 set-up
     L.SolverSetupBoundaryConditions()
     L.setupBoundaryConditions.argtypes = [c_dp, C.c_int, C.c_double]
     L.setupBoundaryConditions(grid, N, h.value)
-    for _ in range(warm):
-        L.ref_vcycle()
-    t0 = time.perf_counter()
-    for _ in range(timed):
-        L.ref_vcycle()
-    dt = time.perf_counter() - t0
-    threads = L.ref_max_threads()
+    last = C.c_double()
+    if warm:
+        L.ref_timed_cycles(warm, C.byref(last))
+    secs = L.ref_timed_cycles(timed, C.byref(last))
     L.ref_solver_close()
-    return dt, threads, N
+    print(json.dumps({"seconds": secs, "threads": threads, "N": N, "last_norm": last.value}))
+    return 0
+
+
+def cpu_reference_cycles(coarse, levels, gs, warm, timed):
+    """(seconds for the timed cycles, threads, N, host cpus) -- in a fresh process with
+    OMP_NUM_THREADS = every CPU this process may run on (torchrun exports
+    OMP_NUM_THREADS=1, which would silently make the OpenMP reference serial)"""
+    env = dict(os.environ)
+    env["OMP_NUM_THREADS"] = str(HOST_CPUS)
+    env.setdefault("OMP_PROC_BIND", "close")   # SURVEY 8(d): CPU baseline plan
+    env.setdefault("OMP_PLACES", "cores")
+    env["OMP_DYNAMIC"] = "false"
+    cmd = [sys.executable, os.path.abspath(__file__), "--cpu-worker", str(coarse), str(levels),
+           str(gs), str(warm), str(timed), str(HOST_CPUS)]
+
+    def widen():  # the child must not inherit a mask some libgomp narrowed in this process
+        try:
+            os.sched_setaffinity(0, HOST_CPU_SET)
+        except OSError:
+            pass
+
+    p = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=3600,
+                       preexec_fn=widen)
+    line = [ln for ln in p.stdout.splitlines() if ln.startswith("{")]
+    if p.returncode != 0 or not line:
+        raise RuntimeError(f"cpu worker failed (rc {p.returncode}): {p.stderr[-500:]}")
+    r = json.loads(line[-1])
+    if "error" in r:
+        raise RuntimeError(r["error"])
+    if HOST_CPUS > 1 and r["threads"] != HOST_CPUS:
+        raise RuntimeError(f"reference ran on {r['threads']} threads, box offers {HOST_CPUS}")
+    return r["seconds"], r["threads"], r["N"]
+
+
+def cpu_baseline_dict(threads, value, sample):
+    return {"value": value, "unit": UNIT, "cores": threads, "kind": "reference",
+            "host_cpus_available": HOST_CPUS, "is_full_node": threads == HOST_CPUS,
+            "sample": sample}
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    os.environ.setdefault("OMP_PROC_BIND", "close")
-    os.environ.setdefault("OMP_PLACES", "cores")
     dt, threads, N = cpu_reference_cycles(COARSE, LEVELS, GS, args.warmup, args.steps)
     dof = float(N) ** 3
     val = dof * args.steps / dt
+    sample = (f"{args.steps} V-cycles of the {N}^3 problem (test_mg_3d {COARSE} {LEVELS} {GS}) after "
+              f"{args.warmup} warm-up, unmodified reference OpenMP code on {threads} host threads, "
+              "timed like test_mg_3d.c:36-68")
+    if args.gpus > 1:
+        sample += (f"; the reference only has cubes: this is one GPU's 513^3 share of the "
+                   f"{args.gpus}-GPU workload, and the metric is per DOF")
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-        "data": "synthetic",
-        "config": {"workload": f"test_mg_3d {COARSE} {LEVELS} {GS}: {N}^3 fp64 Laplace V(2,2)-cycle, "
-                               "reference OpenMP code on host cores"
-                               + ("" if args.gpus == 1 else f" (the reference only has cubes: this is one "
-                                  f"rank's 513^3 share of the {args.gpus}-GPU arm's (512*N+1)x513x513 box; "
-                                  "the metric is per DOF)")},
-        "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "reference",
-                         "sample": f"{args.steps} V-cycles of the {N}^3 problem after {args.warmup} warm-up"},
+        "data": "synthetic", "config": workload_config(args.gpus),
+        "cpu_baseline": cpu_baseline_dict(threads, val, sample),
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -193,145 +266,146 @@ def run_reference(args):
 # --------------------------------------------------------------------------
 # our arm
 # --------------------------------------------------------------------------
+def _leg(fn, *a, **kw):
+    """an extra leg must never cost the headline line"""
+    try:
+        return fn(*a, **kw)
+    except Exception as e:  # pragma: no cover
+        return {"error": f"{type(e).__name__}: {e}"[:400]}
+
+
 def run_ours(args):
-    import numpy as np
-
     import multigrid_parallel_b200 as m
-    from multigrid_parallel_b200.solver import OPT_PROFILE
+    from multigrid_parallel_b200 import benchlib as B
+    from multigrid_parallel_b200 import dist as D
+    from multigrid_parallel_b200 import dist_parity
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if args.gpus != world and world > 1:
-        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
-    if world > 1 or args.problem != "weak":
-        from multigrid_parallel_b200 import dist_bench
-        return dist_bench.run(args, rank, world, local_rank)
+    rank, world, local_rank = D.env_ranks()
+    if args.gpus != world:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch N>1 with "
+                         "python -m torch.distributed.run --nproc-per-node N bench.py --gpus N")
+    D.init_process_group("gloo")
+    warmup = max(args.warmup, 3)
 
-    peak, peak_src = measured_peak_gbs()
-    s = m.Solver(COARSE, LEVELS, GS, device=local_rank)
+    if args.problem == "strong1025":  # stand-alone mode of config 4 (also part of the default line)
+        out = B.strong1025(world, rank, local_rank, steps=args.steps, warmup=warmup)
+        if rank == 0:
+            print(json.dumps({"metric": METRIC, "value": out["dof_cycles_per_s"], "unit": UNIT,
+                              "n_gpus": world, "steps": args.steps, "warmup": warmup,
+                              "ms_per_step": out["ms_per_cycle"], "higher_is_better": True,
+                              "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+                              "data": "synthetic", "config": {"workload": out["workload"]},
+                              "strong1025": out}), flush=True)
+        return 0
+
+    # ---- N > 1: parity first.  No number is printed for a partitioned run that does
+    # not reproduce the single-GPU solver bit for bit.
+    parity = None
+    if world > 1:
+        parity = dist_parity.run_bench_parity(world)
+        if not parity["bitwise"]:
+            if rank == 0:
+                print(json.dumps({"metric": METRIC, "value": None, "unit": UNIT, "n_gpus": world,
+                                  "parity": parity,
+                                  "error": "partitioned solver differs from the single-GPU solver"}),
+                      flush=True)
+            return 1
+
+    # ---- the headline problem
+    coarse = (COARSE,) * 3 if world == 1 else (2 * world + 1, COARSE, COARSE)
+    s = D.make_solver(coarse, LEVELS, GS)
     top = s.levels - 1
-    N = s.dims(top)[2]
-    dof = float(N) ** 3
-
-    def fresh_problem():
-        s.zero(top, m.MGB_U)
-        s.zero(top, m.MGB_D)
-        s.set_dirichlet(top, m.MGB_D)
-        s.set_dirichlet(top, m.MGB_U)
-
-    fresh_problem()
-    init = math.sqrt(s.sumsq(top, m.MGB_D))
-    for _ in range(max(args.warmup, 3)):
-        s.vcycle()
-    s.sync()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
-    l0 = s.launch_count
-    s.timer_start()
-    for _ in range(args.steps):
-        s.vcycle()
-    dt = s.timer_stop()
-    launches = s.launch_count - l0
-    clocks = sampler.finish()
+    ni, nj, nk = s.dims(top)
+    dof = float(ni) * nj * nk
+    init = B.fresh_problem(s)
+    sampler = None
+    if rank == 0:
+        sampler = ClockSampler(local_rank)
+        sampler.start()
+    dt, launches = B.time_cycles(s, args.steps, warmup)
+    clocks = sampler.finish() if sampler else None
     value = dof * args.steps / dt
 
-    # dominant kernel, live: the same cycles with per-stage CUDA events; the
-    # smoother stages of the finest level are 2*gs half-sweep launches each
-    s.set_option(OPT_PROFILE, 1)
-    s.vcycle()
-    s.timing_reset()
-    prof_cycles = max(3, min(args.steps, 10))
-    for _ in range(prof_cycles):
-        s.vcycle()
-    stage = {st: s.timing(top, st)[1] / prof_cycles for st in range(7)}
-    s.set_option(OPT_PROFILE, 0)
-    n_half = 2 * GS * 2  # launches per cycle on the finest level (pre + post)
-    t_half = (stage[0] + stage[5]) / n_half
-    achieved = HALF_SWEEP_BYTES_PER_DOF * dof / t_half / 1e9
-    share = (stage[0] + stage[5]) / (sum(stage[st] for st in range(7)))
-    others = {}
-    for st in range(7):
-        name = m.STAGE_NAMES[st]
-        if name in STAGE_BYTES_PER_DOF and stage[st] > 0:
-            kern, what, bpd = STAGE_BYTES_PER_DOF[name]
-            gbs = bpd * dof / stage[st] / 1e9
-            others[kern] = {"what": what, "achieved": gbs, "frac": gbs / peak, "bytes_per_dof": bpd,
-                            "launch_us": stage[st] * 1e6, "traffic": ncu_traffic(kern)}
+    stage_us = None
+    if world == 1:
+        roofline, stage_us = B.stage_roofline_single(s, max(3, min(args.steps, 10)))
+    else:
+        roofline = B.stage_roofline_dist(s, rank)
 
-    # end to end through the C ABI with host buffers (pinned), whole solve
-    import torch
-    hu = torch.zeros((N, N, N), dtype=torch.float64).pin_memory()
-    hd = torch.zeros((N, N, N), dtype=torch.float64).pin_memory()
-    # host copies of the problem (faces = BCFunc, interior 0), produced once
-    fresh_problem()
-    s.download_ptr(top, m.MGB_U, hu.data_ptr())
-    s.download_ptr(top, m.MGB_D, hd.data_ptr())
-    u0 = hu.clone().pin_memory()
-    thr = init * TOL
-    e2e_times, cycles = [], 0
-    for rep in range(3):
-        hu.copy_(u0)
-        t0 = time.perf_counter()
-        s.upload_ptr(top, m.MGB_U, hu.data_ptr())
-        s.upload_ptr(top, m.MGB_D, hd.data_ptr())
-        hist = s.solve(thr, 100)
-        s.download_ptr(top, m.MGB_U, hu.data_ptr())
-        e2e_times.append(time.perf_counter() - t0)
-        cycles = len(hist)
-    t_e2e = min(e2e_times[1:])
-    e2e_val = dof * cycles / t_e2e
+    t_e2e, hist, slab_bytes = B.e2e_solve(s, init)
+    cycles = len(hist)
+    first_dist = s.first_dist_level if world > 1 else None
+    s.close()
+
+    # ---- the other BASELINE configs
+    rbgs = None
+    if world == 1:
+        rbgs = {"flow": "test_rb_gs_3d.c:56-101: preSmoother(.,1) + postSmoother(.,1) per iteration "
+                        "on one resident grid, rhs 0, Dirichlet faces",
+                "257": _leg(B.rbgs, 257, 200, local_rank), "513": _leg(B.rbgs, 513, 40, local_rank),
+                "target": ">= 0.70 of the 8 TB/s nominal HBM peak (BASELINE north_star)"}
+    strong = None if args.no_extras else _leg(B.strong1025, world, rank, local_rank)
+    c5 = None if args.no_extras else _leg(B.config5, world)
 
     cpu = None
-    if not args.no_cpu_baseline:
+    if rank == 0 and not args.no_cpu_baseline:
         try:
             cdt, threads, _ = cpu_reference_cycles(COARSE, LEVELS, GS, 1, 3)
-            cpu = {"value": dof * 3 / cdt, "unit": UNIT, "cores": threads, "kind": "reference",
-                   "sample": f"3 V-cycles of the same {N}^3 problem after 1 warm-up, reference OpenMP "
-                             "code (oracle/_ref) on this box's host cores"}
+            cpu = cpu_baseline_dict(threads, 513.0 ** 3 * 3 / cdt,
+                                    "3 V-cycles of the 513^3 problem (test_mg_3d 3 9 2) after 1 warm-up, "
+                                    "unmodified reference OpenMP code (oracle/_ref) on this box's host "
+                                    "threads, timed like test_mg_3d.c:36-68")
         except Exception as e:
             cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference",
                    "sample": f"unavailable: {e}"}
 
-    line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps,
-        "warmup": max(args.warmup, 3), "ms_per_step": 1e3 * dt / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-        "data": "synthetic",
-        "config": {"workload": f"test_mg_3d {COARSE} {LEVELS} {GS}: {N}^3 fp64 Laplace V(2,2)-cycle, "
-                               "Dirichlet x^2-2y^2+z^2, coarse 3^3 LU",
-                   "l2": "inputs larger than L2 (3 x 1.1 GB level arrays vs 126 MB)",
-                   "cycles_to_1e-8": cycles, "final_residual": float(hist[-1])},
-        "clocks": clocks,
-        "gpu_launches": int(launches),
-        "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": int(2 * dof * 8),
-                "d2h_bytes_per_step": int(dof * 8), "seconds_per_solve": t_e2e, "cycles": cycles,
-                "step": "one full solve: upload grid+rhs from pinned host memory, V-cycles to "
-                        "1e-8*||d||, download grid"},
-        "roofline": {"bound": "hbm", "kernel": "k_tile_sweep (RB-GS half-sweep, TMA ring)", "achieved": achieved, "peak": peak,
-                     "unit": "GB/s", "frac": achieved / peak, "traffic": ncu_traffic("k_tile_sweep<1,6,43>"),
-                     "peak_source": peak_src, "bytes_per_dof": HALF_SWEEP_BYTES_PER_DOF,
-                     "avg_launch_us": t_half * 1e6, "share_of_finest_level": share,
-                     "frac_of_8TBs_nominal": achieved / 8000.0,
-                     "other_kernels": others},
-        "stage_us_finest": {m.STAGE_NAMES[st]: stage[st] * 1e6 for st in range(7)},
-        "cpu_baseline": cpu,
-    }
-    print(json.dumps(line), flush=True)
-    s.close()
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(world),
+            "convergence": {"cycles_to_1e-8": cycles, "final_residual": float(hist[-1]),
+                            "grid": f"{ni}x{nj}x{nk}", "first_partitioned_level": first_dist},
+            "clocks": clocks, "gpu_launches": int(launches),
+            "e2e": {"value": dof * cycles / t_e2e, "unit": UNIT,
+                    "h2d_bytes_per_step": int(2 * slab_bytes * world),
+                    "d2h_bytes_per_step": int(slab_bytes * world), "seconds_per_solve": t_e2e,
+                    "cycles": cycles,
+                    "step": "one full solve through the C ABI: every rank uploads its grid+rhs slab "
+                            "from pinned host memory, V-cycles to 1e-8*||d||, every rank downloads "
+                            "its grid slab"},
+            "roofline": roofline, "cpu_baseline": cpu,
+        }
+        if stage_us is not None:
+            line["stage_us_finest"] = stage_us
+        if parity is not None:
+            line["parity"] = parity
+        if rbgs is not None:
+            line["rbgs"] = rbgs
+        if strong is not None:
+            line["strong1025"] = strong
+        if c5 is not None:
+            line["config5"] = c5
+        print(json.dumps(line), flush=True)
+    D.barrier()
     return 0
 
 
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "--cpu-worker":
+        return cpu_worker(sys.argv[2:])
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true",
+                    help="skip the strong1025 / config5 legs (quick runs, profiling)")
     ap.add_argument("--problem", default="weak", choices=["weak", "strong1025"],
-                    help="weak (default): 513^3 per GPU; strong1025: the 1025^3 cube of BASELINE "
-                         "config 4 on --gpus GPUs (extra mode, no e2e leg)")
+                    help="weak (default): 513^3 per GPU; strong1025: only the 1025^3 cube of "
+                         "BASELINE config 4 on --gpus GPUs")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

@@ -125,8 +125,14 @@ int mgb_prolong_correct(mgb_solver *s, int level);
 int mgb_sweep_residual_restrict(mgb_solver *s, int level, int colour);
 int mgb_sweep_residual(mgb_solver *s, int level, int colour, double *sumsq);
 int mgb_coarse_solve(mgb_solver *s);
-/* the factorised coarse operator, row-major n x n (n = ci*cj*ck) */
+/* the factorised coarse operator, row-major n x n (n = ci*cj*ck): what
+ * convertToLU_InPlace leaves in `A` (gauss_elim.h:9-29), bit for bit */
 int mgb_coarse_lu_download(mgb_solver *s, double *host_lu);
+/* size of the coarsest system, the half bandwidth (cj*ck) the factorisation and
+ * the solves are restricted to (exact: see csrc/lu.cu), and the device time the
+ * build + factorisation took at mgb_create (the reference's
+ * constructCoarseMatrixA + convertToLU_InPlace, mg_3d.h:281-288) */
+int mgb_coarse_info(const mgb_solver *s, int *n, int *half_bandwidth, double *factor_seconds);
 
 /* ---- the V-cycle ---------------------------------------------------------
  * mgb_vcycle = SolverLinSolve -> vcycle (mg_3d.h:1415-1420, 1242-1362): one

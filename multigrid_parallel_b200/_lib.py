@@ -73,6 +73,7 @@ def load_library():
     L.mgb_sweep_residual.argtypes = [vp, i, i, c_dp]
     L.mgb_coarse_solve.argtypes = [vp]
     L.mgb_coarse_lu_download.argtypes = [vp, C.c_void_p]
+    L.mgb_coarse_info.argtypes = [vp, c_ip, c_ip, c_dp]
     L.mgb_vcycle.argtypes = [vp, c_dp]
     L.mgb_solve.argtypes = [vp, d, i, c_dp, c_ip]
     L.mgb_timing.argtypes = [vp, i, i, c_ip, c_dp]

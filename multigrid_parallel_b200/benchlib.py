@@ -1,0 +1,269 @@
+"""Measurement legs of bench.py, for one GPU and for N GPUs (one process per GPU).
+
+Every leg goes through the C ABI (libmgb.so via the ctypes mirror); times are
+CUDA events on the solver's own stream (mgb_timer_start/stop), max over ranks.
+No CPU checker and no reference code is involved here (bench.py times those itself).
+
+  main_problem   the headline V-cycle problem (513^3 per GPU)
+  stage_roofline per-stage CUDA-event times of the finest level (1 GPU) or the
+                 half-sweep incl. its halo exchange per GPU (N GPUs)
+  e2e_solve      whole solve from pinned host buffers and back
+  rbgs           BASELINE config 2: RB-GS sweeps alone, 257^3 and 513^3
+  strong1025     BASELINE config 4: the 1025^3 cube on N GPUs (+ 1 GPU for the ratio)
+  config5        BASELINE config 5: 1025 x 1025 x (256N+1), coarse 9 x 9 x (2N+1) dense LU
+"""
+import json
+import math
+import os
+import time
+
+from . import dist as D
+from .solver import MGB_D, MGB_U, OPT_PROFILE, STAGE_NAMES, Solver
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+TOL = 1e-8                       # test_mg_3d.c:19
+HALF_SWEEP_BYTES_PER_DOF = 12.0  # read 1/2 v, read 1/2 d, write 1/2 v
+# SURVEY 8(d) algorithmic bytes per DOF of the other finest-level stages:
+# stage -> (kernel as named in profiles/traffic.json, what it is, bytes per DOF)
+STAGE_BYTES_PER_DOF = {
+    "CalcResidual1": ("k_tile<-1,1,2,11,34>", "residual+restrict (TMA tile kernel)", 17.0),
+    # inside the cycle only the red points are corrected (the post-smoother's first
+    # half-sweep overwrites the black ones): 1 + 4 + 4 B/DOF
+    "Prolongate&Correct": ("k_tile_prolong_one<1>", "prolongation+correction of the red points "
+                           "(TMA ring)", 9.0),
+    "CalcResidual2": ("k_tile<-1,0,2,5,43>", "residual norm (TMA tile kernel)", 16.0),
+}
+
+
+def measured_peak_gbs():
+    try:
+        return (float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]),
+                "measured (MEASURED_PEAKS.json)")
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic(kernel):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` from the
+    committed `ncu --set full` capture (profiles/traffic.json), or None"""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        return t[kernel]["dram_bytes_per_launch"]
+    except Exception:
+        return None
+
+
+def fresh_problem(s):
+    """the test_mg_3d.c problem on the finest level: u = d = 0 inside, BCFunc on the faces"""
+    top = s.levels - 1
+    s.zero(top, MGB_U)
+    s.zero(top, MGB_D)
+    s.set_dirichlet(top, MGB_D)
+    s.set_dirichlet(top, MGB_U)
+    return math.sqrt(s.sumsq(top, MGB_D))
+
+
+def time_cycles(s, steps, warmup):
+    """`steps` V-cycles after `warmup`; device seconds (max over ranks), launches"""
+    for _ in range(warmup):
+        s.vcycle()
+    s.sync()
+    l0 = s.launch_count
+    D.barrier()
+    s.sync()
+    s.timer_start()
+    for _ in range(steps):
+        s.vcycle()
+    dt = D.max_over_ranks(s.timer_stop())
+    D.barrier()
+    return dt, s.launch_count - l0
+
+
+def stage_roofline_single(s, prof_cycles):
+    """1 GPU: the same cycles with per-stage CUDA events (eager launches); the smoother
+    stages of the finest level are 2*gs half-sweep launches each"""
+    peak, peak_src = measured_peak_gbs()
+    top = s.levels - 1
+    ni, nj, nk = s.dims(top)
+    dof = float(ni) * nj * nk
+    s.set_option(OPT_PROFILE, 1)
+    s.vcycle()
+    s.timing_reset()
+    for _ in range(prof_cycles):
+        s.vcycle()
+    stage = {st: s.timing(top, st)[1] / prof_cycles for st in range(7)}
+    s.set_option(OPT_PROFILE, 0)
+    n_half = 2 * s.gs * 2  # launches per cycle on the finest level (pre + post)
+    t_half = (stage[0] + stage[5]) / n_half
+    achieved = HALF_SWEEP_BYTES_PER_DOF * dof / t_half / 1e9
+    share = (stage[0] + stage[5]) / sum(stage.values())
+    others = {}
+    for st in range(7):
+        name = STAGE_NAMES[st]
+        if name in STAGE_BYTES_PER_DOF and stage[st] > 0:
+            kern, what, bpd = STAGE_BYTES_PER_DOF[name]
+            gbs = bpd * dof / stage[st] / 1e9
+            others[kern] = {"what": what, "achieved": gbs, "frac": gbs / peak, "bytes_per_dof": bpd,
+                            "launch_us": stage[st] * 1e6, "traffic": ncu_traffic(kern),
+                            "traffic_source": "static ncu capture (profiles/traffic.json)"}
+    roofline = {"bound": "hbm", "kernel": "k_tile_sweep<c,6,43> (RB-GS half-sweep, TMA ring)",
+                "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": ncu_traffic("k_tile_sweep<1,6,43>"),
+                "traffic_source": "static ncu capture (profiles/traffic.json)",
+                "peak_source": peak_src, "bytes_per_dof": HALF_SWEEP_BYTES_PER_DOF,
+                "avg_launch_us": t_half * 1e6, "share_of_finest_level": share,
+                "frac_of_8TBs_nominal": achieved / 8000.0, "other_kernels": others}
+    return roofline, {STAGE_NAMES[st]: stage[st] * 1e6 for st in range(7)}
+
+
+def stage_roofline_dist(s, rank):
+    """N GPUs: the half-sweep on this rank's slab of the finest level, timed with its halo
+    exchange as the cycle runs it"""
+    peak, peak_src = measured_peak_gbs()
+    top = s.levels - 1
+    ni, nj, nk = s.dims(top)
+    i0, li, own_lo, own_hi = s.local_range(top)
+    for _ in range(2):
+        s.half_sweep(top, 1)
+        s.half_sweep(top, 0)
+    s.sync()
+    D.barrier()
+    s.timer_start()
+    nrep = 10
+    for _ in range(nrep):
+        s.half_sweep(top, 1)
+        s.half_sweep(top, 0)
+    t_half = D.max_over_ranks(s.timer_stop()) / (2 * nrep)
+    own_planes = own_hi - own_lo
+    local_dof = float(own_planes) * nj * nk
+    achieved = HALF_SWEEP_BYTES_PER_DOF * local_dof / t_half / 1e9
+    return {"bound": "hbm", "kernel": "k_tile_sweep<c,6,43> (RB-GS half-sweep, TMA ring) + its halo "
+                                      "exchange over NVLink peer memory",
+            "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+            "traffic": None, "peak_source": peak_src, "bytes_per_dof": HALF_SWEEP_BYTES_PER_DOF,
+            "avg_launch_us": t_half * 1e6,
+            "note": f"per GPU, rank {rank}'s slab of {own_planes} planes; time = slowest rank, "
+                    "half-sweep incl. pushing its boundary planes and waiting for the neighbours'"}
+
+
+def e2e_solve(s, init, reps=3):
+    """whole solve through the ABI from pinned host arrays: upload grid + rhs slab,
+    V-cycles to 1e-8*||d||, download the grid slab; wall clock, max over ranks"""
+    import torch
+    top = s.levels - 1
+    shape = s.local_shape(top)
+    hu = torch.zeros(shape, dtype=torch.float64).pin_memory()
+    hd = torch.zeros(shape, dtype=torch.float64).pin_memory()
+    fresh_problem(s)
+    s.download_ptr(top, MGB_U, hu.data_ptr())
+    s.download_ptr(top, MGB_D, hd.data_ptr())
+    u0 = hu.clone().pin_memory()
+    times, hist = [], [0.0]
+    for _ in range(reps):
+        hu.copy_(u0)
+        D.barrier()
+        t0 = time.perf_counter()
+        s.upload_ptr(top, MGB_U, hu.data_ptr())
+        s.upload_ptr(top, MGB_D, hd.data_ptr())
+        hist = s.solve(init * TOL, 100)
+        s.download_ptr(top, MGB_U, hu.data_ptr())
+        times.append(D.max_over_ranks(time.perf_counter() - t0))
+    slab_bytes = float(shape[0]) * shape[1] * shape[2] * 8
+    return min(times[1:]), hist, slab_bytes
+
+
+def rbgs(n, iters, device):
+    """BASELINE config 2 (test_rb_gs_3d.c:56-101 flow): preSmoother(.,1) + postSmoother(.,1)
+    per iteration on ONE resident grid = 2 full sweeps = 48 B/DOF"""
+    peak, _ = measured_peak_gbs()
+    with Solver(n, 1, 1, device=device) as s:
+        dof = float(n) ** 3
+        s.set_dirichlet(0, MGB_U)
+        for _ in range(5):
+            s.smooth(0, 1, True)
+            s.smooth(0, 1, False)
+        s.sync()
+        s.timer_start()
+        for _ in range(iters):
+            s.smooth(0, 1, True)
+            s.smooth(0, 1, False)
+        sec = s.timer_stop()
+        res = s.residual(0)
+    gbs = 24.0 * dof * 2 * iters / sec / 1e9
+    return {"grid": f"{n}^3", "full_sweeps": 2 * iters, "us_per_full_sweep": sec / (2 * iters) * 1e6,
+            "gbs": gbs, "frac_of_measured_peak": gbs / peak, "frac_of_8TBs_nominal": gbs / 8000.0,
+            "bytes_per_dof_per_full_sweep": 24.0, "residual_after": res}
+
+
+def _cycle_ms(coarse, levels, gs, steps, warmup, solve=True, device=None, single=False):
+    """ms per V-cycle of a fresh test_mg_3d-type problem on the current ranks (or, with
+    single=True, on this process's GPU alone)"""
+    s = Solver(coarse, levels, gs, device=device) if single else D.make_solver(coarse, levels, gs)
+    try:
+        init = fresh_problem(s)
+        if single:
+            for _ in range(warmup):
+                s.vcycle()
+            s.sync()
+            s.timer_start()
+            for _ in range(steps):
+                s.vcycle()
+            dt = s.timer_stop()
+        else:
+            dt, _ = time_cycles(s, steps, warmup)
+        out = {"ms_per_cycle": 1e3 * dt / steps, "first_partitioned_level":
+               (None if single or s.nranks == 1 else s.first_dist_level)}
+        ni, nj, nk = s.dims(levels - 1)
+        out["grid"] = f"{ni}x{nj}x{nk}"
+        out["dof_cycles_per_s"] = float(ni) * nj * nk * steps / dt
+        if solve:
+            fresh_problem(s)
+            hist = s.solve(init * TOL, 100)
+            out["cycles_to_1e-8"] = len(hist)
+            out["final_residual"] = float(hist[-1])
+        n, bw, fsec = s.coarse_info()
+        out["coarse_unknowns"], out["coarse_half_bandwidth"] = n, bw
+        out["lu_factor_ms"] = fsec * 1e3
+        # the coarsest solve alone (one launch per cycle, on the rank(s) that own level 0)
+        for _ in range(3):
+            s.coarse_solve()
+        s.sync()
+        s.timer_start()
+        for _ in range(20):
+            s.coarse_solve()
+        out["lu_solve_us"] = s.timer_stop() / 20 * 1e6
+        return out
+    finally:
+        s.close()
+
+
+def strong1025(world, rank, local_rank, steps=10, warmup=3):
+    """BASELINE config 4: the SAME 1025^3 cube (3 10 2) on `world` GPUs; the 1-GPU time the
+    speed-up is quoted against is measured in the same run (on rank 0's GPU)"""
+    out = _cycle_ms((3, 3, 3), 10, 2, steps, warmup)
+    out["workload"] = "test_mg_3d 3 10 2: 1025^3 fp64 Laplace V(2,2)-cycle, strong scaling"
+    out["n_gpus"] = world
+    if world > 1:
+        one = None
+        if rank == 0:
+            one = _cycle_ms((3, 3, 3), 10, 2, 5, 2, solve=True, device=local_rank, single=True)
+        D.barrier()
+        one = D.broadcast_bytes(one, 0)
+        out["one_gpu_ms_per_cycle"] = one["ms_per_cycle"]
+        out["one_gpu_final_residual"] = one.get("final_residual")
+        out["speedup_vs_1gpu"] = one["ms_per_cycle"] / out["ms_per_cycle"]
+        out["target_speedup_at_8"] = 6.0
+    return out
+
+
+def config5(world, steps=10, warmup=3):
+    """BASELINE config 5: weak scaling 1025 x 1025 x (256*N+1) per N GPUs (the slab axis is
+    the reference's slowest index i, so the extents read (256N+1) x 1025 x 1025), 8 levels,
+    coarsest grid (2N+1) x 9 x 9 = 81(2N+1) unknowns solved by the dense-LU path of
+    gauss_elim.h every cycle"""
+    out = _cycle_ms((2 * world + 1, 9, 9), 8, 2, steps, warmup)
+    out["workload"] = (f"{256 * world + 1}x1025x1025 fp64 Laplace V(2,2)-cycle, coarse "
+                       f"{2 * world + 1}x9x9 LU ({81 * (2 * world + 1)} unknowns), 8 levels")
+    out["n_gpus"] = world
+    out["lu_solve_share_of_cycle"] = out["lu_solve_us"] * 1e-3 / out["ms_per_cycle"]
+    return out

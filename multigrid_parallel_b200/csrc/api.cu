@@ -135,7 +135,9 @@ struct mgb_solver {
     size_t stage_n = 0;
     // coarsest operator
     int nc = 0;
-    double *lu = nullptr, *lut = nullptr, *cb = nullptr, *cx = nullptr;
+    double *lu = nullptr;      // dense factor (what the reference calls A after LU)
+    LuBand band{};             // the same factor in band form: what the solve reads
+    double factor_secs = 0.;   // device time of build + factorisation (once, at create)
     // options
     int opt_graph = 1, opt_profile = 0, opt_fuse = 1;
     // levels 0..tail_top (<= ~33^3) run as ONE kernel (tail.cu); -1: none
@@ -177,6 +179,10 @@ struct mgb_solver {
     int opt_p2p = 1;
     PeerSide low, up;
     unsigned long long *xflags = nullptr;
+    // a halo wait that gives up (MGB_HALO_TIMEOUT_S, default 300 s, 0 = never) sets
+    // bits here (host-mapped) instead of trapping; checked after every synchronisation
+    unsigned int *h_halo_err = nullptr, *d_halo_err = nullptr;
+    unsigned long long halo_timeout_ns = 300ULL * 1000000000ULL;
     bool is_dist() const { return nranks > 1; }
     // does this rank compute on level q?
     bool works_on(int q) const { return nranks == 1 || q >= LD || rank == 0; }
@@ -195,6 +201,20 @@ static int bind(const mgb_solver *s)
         return fail("null solver");
     CK(cudaSetDevice(s->device));
     return 0;
+}
+
+// after a synchronisation: did a halo wait give up on a neighbour?
+static int halo_status(mgb_solver *s)
+{
+    if (!s->h_halo_err || !*s->h_halo_err)
+        return 0;
+    const unsigned int e = *s->h_halo_err;
+    *s->h_halo_err = 0;
+    return fail("rank %d: halo exchange timed out after %.0f s waiting for the %s%s%s neighbour "
+                "(MGB_HALO_TIMEOUT_S; all array-changing calls of a partitioned solver are "
+                "collective over the ranks); the level arrays are no longer consistent",
+                s->rank, 1e-9 * (double)s->halo_timeout_ns, (e & 1) ? "lower" : "",
+                (e & 3) == 3 ? " and " : "", (e & 2) ? "upper" : "");
 }
 
 static int check_level(const mgb_solver *s, int level, int which)
@@ -216,6 +236,13 @@ extern "C" int mgb_destroy(mgb_solver *s)
     cudaSetDevice(s->device);
     if (s->st)
         cudaStreamSynchronize(s->st);
+    if (s->comm && s->xflags) {
+        // collective: the neighbours have my arrays mapped (CUDA IPC) and may still be
+        // pushing into them; nobody frees anything before everybody has got here
+        nccl().AllReduce(s->xflags + 8, s->xflags + 8, 1, ncclInt, ncclSum, s->comm, s->st);
+        cudaStreamSynchronize(s->st);
+    }
+    if (s->h_halo_err) cudaFreeHost(s->h_halo_err);
     if (s->gexec)
         cudaGraphExecDestroy(s->gexec);
     for (auto &l : s->lv)
@@ -230,9 +257,9 @@ extern "C" int mgb_destroy(mgb_solver *s)
     if (s->h_scal) cudaFreeHost(s->h_scal);
     if (s->stage) cudaFree(s->stage);
     if (s->lu) cudaFree(s->lu);
-    if (s->lut) cudaFree(s->lut);
-    if (s->cb) cudaFree(s->cb);
-    if (s->cx) cudaFree(s->cx);
+    if (s->band.lb) cudaFree(s->band.lb);
+    if (s->band.ub) cudaFree(s->band.ub);
+    if (s->band.ud) cudaFree(s->band.ud);
     for (PeerSide *ps : {&s->low, &s->up})
         for (void *p : ps->opened)
             cudaIpcCloseMemHandle(p);
@@ -558,16 +585,30 @@ static int create_impl(mgb_solver **out, int ci, int cj, int ck, int levels, int
     const long long nc = (long long)ci * cj * ck;
     if (nc <= MGB_MAX_DENSE_N) {
         s->nc = (int)nc;
+        // half bandwidth of the 7-point operator in the ordering p = (i*nj+j)*nk+k
+        s->band.n = s->nc;
+        s->band.bw = cj * ck < s->nc - 1 ? cj * ck : s->nc - 1;
+        const size_t bn = (size_t)s->band.bw * nc;
         CKD(cudaMalloc(&s->lu, sizeof(double) * nc * nc));
-        CKD(cudaMalloc(&s->lut, sizeof(double) * nc * nc));
-        CKD(cudaMalloc(&s->cb, sizeof(double) * nc));
-        CKD(cudaMalloc(&s->cx, sizeof(double) * nc));
+        CKD(cudaMalloc(&s->band.lb, sizeof(double) * (bn ? bn : 1)));
+        CKD(cudaMalloc(&s->band.ub, sizeof(double) * (bn ? bn : 1)));
+        CKD(cudaMalloc(&s->band.ud, sizeof(double) * nc));
         LaunchScope ls(s);
+        cudaEvent_t e0, e1;
+        CKD(cudaEventCreate(&e0));
+        CKD(cudaEventCreate(&e1));
+        CKD(cudaEventRecord(e0, s->st));
         launch_coarse_matrix(s->lu, ci, cj, ck, s->lv[0].h, s->st);
-        launch_lu_factor(s->lu, s->nc, s->st);
-        launch_transpose(s->lu, s->lut, s->nc, s->st);
+        launch_lu_factor_band(s->lu, s->nc, s->band.bw, s->st);
+        launch_lu_extract_band(s->lu, s->band, s->st);
+        CKD(cudaEventRecord(e1, s->st));
         CKD(cudaGetLastError());
         CKD(cudaStreamSynchronize(s->st));
+        float ms = 0.f;
+        CKD(cudaEventElapsedTime(&ms, e0, e1));
+        s->factor_secs = 1e-3 * ms;
+        cudaEventDestroy(e0);
+        cudaEventDestroy(e1);
     } else if (levels > 1) {
         mgb_destroy(s);
         return fail("coarsest grid has %lld unknowns > MGB_MAX_DENSE_N", nc);
@@ -594,6 +635,11 @@ static int create_impl(mgb_solver **out, int ci, int cj, int ck, int levels, int
         }
         if (getenv("MGB_P2P"))
             s->opt_p2p = atoi(getenv("MGB_P2P")) != 0;
+        if (getenv("MGB_HALO_TIMEOUT_S"))
+            s->halo_timeout_ns = (unsigned long long)(atof(getenv("MGB_HALO_TIMEOUT_S")) * 1e9);
+        CKD(cudaHostAlloc(&s->h_halo_err, sizeof(unsigned int), cudaHostAllocMapped));
+        *s->h_halo_err = 0;
+        CKD(cudaHostGetDevicePointer(&s->d_halo_err, s->h_halo_err, 0));
         if (s->opt_p2p && setup_p2p(s)) {
             mgb_destroy(s);
             return 1;
@@ -764,7 +810,7 @@ extern "C" int mgb_sync(mgb_solver *s)
     if (bind(s))
         return 1;
     CK(cudaStreamSynchronize(s->st));
-    return 0;
+    return halo_status(s);
 }
 
 // ----------------------------------------------------------------------------
@@ -805,7 +851,7 @@ extern "C" int mgb_upload(mgb_solver *s, int level, int which, const double *hos
     halo_fence(s, lv);
     CKLAUNCH();
     CK(cudaStreamSynchronize(s->st));
-    return 0;
+    return halo_status(s);
 }
 
 extern "C" int mgb_download(mgb_solver *s, int level, int which, double *host)
@@ -953,7 +999,8 @@ static void halo_step(mgb_solver *s, Level &lv, double *a, int mask, int send_up
         if (phase != HALO_PUSH) {
             const bool wl = has_low && recv_low >= 0, wu = has_up && recv_up >= 0;
             launch_halo_wait(wl ? s->xflags + 0 : nullptr, s->xflags + 4,
-                             wu ? s->xflags + 1 : nullptr, s->xflags + 5, s->st);
+                             wu ? s->xflags + 1 : nullptr, s->xflags + 5, s->halo_timeout_ns,
+                             s->d_halo_err, s->st);
         }
         s->nccl_calls++;
         return;
@@ -1018,7 +1065,7 @@ static int fetch_scalar(mgb_solver *s, int slot, double *out)
                        cudaMemcpyDeviceToHost, s->st));
     CK(cudaStreamSynchronize(s->st));
     *out = s->h_scal[slot];
-    return 0;
+    return halo_status(s);
 }
 
 extern "C" int mgb_sumsq(mgb_solver *s, int level, int which, double *sumsq)
@@ -1262,9 +1309,7 @@ static void q_coarse_solve(mgb_solver *s)
     if (!s->works_on(0))
         return;
     Level &lv = s->lv[0];
-    launch_unpack(lv.g, lv.a[MGB_D].base, s->cb, s->st);
-    launch_lu_solve(s->lu, s->lut, s->nc, s->cb, s->cx, s->st);
-    launch_pack(lv.g, s->cx, lv.a[MGB_U].base, s->st);
+    launch_lu_solve_level(s->band, lv.g, lv.a[MGB_D].base, lv.a[MGB_U].base, s->st);
 }
 
 #define OP_PROLOGUE(level_expr, min_level)                                        \
@@ -1366,6 +1411,17 @@ extern "C" int mgb_coarse_solve(mgb_solver *s)
     return 0;
 }
 
+extern "C" int mgb_coarse_info(const mgb_solver *s, int *n, int *half_bandwidth,
+                               double *factor_seconds)
+{
+    if (!s)
+        return fail("null solver");
+    if (n) *n = s->nc;
+    if (half_bandwidth) *half_bandwidth = s->band.bw;
+    if (factor_seconds) *factor_seconds = s->factor_secs;
+    return 0;
+}
+
 extern "C" int mgb_coarse_lu_download(mgb_solver *s, double *host_lu)
 {
     if (bind(s))
@@ -1430,9 +1486,7 @@ static void enqueue_cycle(mgb_solver *s, int q, bool timed)
         p.top = q;
         p.gs = s->gs;
         p.zero_top = 1;
-        p.nc = s->nc;
-        p.lu = s->lu;
-        p.lut = s->lut;
+        p.lu = s->band;
         for (int l = 0; l <= q; l++) {
             Level &t = s->lv[l];
             p.lv[l] = TailLevel{t.g, t.a[MGB_U].base, t.a[MGB_D].base, t.a[MGB_R].base, t.hSq,
@@ -1854,7 +1908,7 @@ extern "C" int mgb_host_lu_factor(double *a, int n)
     Scratch d;
     CK(cudaMalloc(&d.p, sizeof(double) * (size_t)n * n));
     CK(cudaMemcpy(d.p, a, sizeof(double) * (size_t)n * n, cudaMemcpyHostToDevice));
-    launch_lu_factor(d.p, n, 0);
+    launch_lu_factor_band(d.p, n, lu_bandwidth(d.p, n, 0), 0);
     CKLAUNCH();
     CK(cudaMemcpy(a, d.p, sizeof(double) * (size_t)n * n, cudaMemcpyDeviceToHost));
     return 0;
@@ -1866,15 +1920,25 @@ extern "C" int mgb_host_lu_solve(const double *lu, int n, const double *b, doubl
         return 1;
     if (n > MGB_MAX_DENSE_N)
         return fail("n=%d exceeds MGB_MAX_DENSE_N", n);
-    Scratch d, t, vb, vx;
+    if (n < 1)
+        return fail("n < 1");
+    Scratch d, lb, ub, ud, vb, vx;
     CK(cudaMalloc(&d.p, sizeof(double) * (size_t)n * n));
-    CK(cudaMalloc(&t.p, sizeof(double) * (size_t)n * n));
     CK(cudaMalloc(&vb.p, sizeof(double) * n));
     CK(cudaMalloc(&vx.p, sizeof(double) * n));
     CK(cudaMemcpy(d.p, lu, sizeof(double) * (size_t)n * n, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(vb.p, b, sizeof(double) * n, cudaMemcpyHostToDevice));
-    launch_transpose(d.p, t.p, n, 0);
-    launch_lu_solve(d.p, t.p, n, vb.p, vx.p, 0);
+    // zeros (of either sign) outside the band of the factor contribute nothing
+    LuBand B{};
+    B.n = n;
+    B.bw = lu_bandwidth(d.p, n, 0);
+    const size_t bn = (size_t)B.bw * n;
+    CK(cudaMalloc(&lb.p, sizeof(double) * (bn ? bn : 1)));
+    CK(cudaMalloc(&ub.p, sizeof(double) * (bn ? bn : 1)));
+    CK(cudaMalloc(&ud.p, sizeof(double) * n));
+    B.lb = lb.p; B.ub = ub.p; B.ud = ud.p;
+    launch_lu_extract_band(d.p, B, 0);
+    launch_lu_solve_dense(B, vb.p, vx.p, 0);
     CKLAUNCH();
     CK(cudaMemcpy(x, vx.p, sizeof(double) * n, cudaMemcpyDeviceToHost));
     return 0;

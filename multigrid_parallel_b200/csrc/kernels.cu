@@ -1199,9 +1199,21 @@ __global__ void __launch_bounds__(256) k_halo_push(HaloDir up, HaloDir low)
     }
 }
 
-// thread 0 waits for flag0 (if any), thread 1 for flag1 (if any)
+__device__ __forceinline__ unsigned long long global_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+// thread 0 waits for flag0 (if any), thread 1 for flag1 (if any).  A neighbour
+// that never shows up must not hang the GPU for ever, nor poison the context
+// with a trap: after `timeout_ns` (wall clock, %globaltimer; 0 = wait for ever)
+// the waiter records which side it gave up on in *err (pinned host memory, read
+// by the host after the next synchronisation) and lets the stream go on.
 __global__ void k_halo_wait(const unsigned long long *flag0, unsigned long long *expect0,
-                            const unsigned long long *flag1, unsigned long long *expect1)
+                            const unsigned long long *flag1, unsigned long long *expect1,
+                            unsigned long long timeout_ns, unsigned int *err)
 {
     const unsigned long long *flag = threadIdx.x == 0 ? flag0 : flag1;
     unsigned long long *expect = threadIdx.x == 0 ? expect0 : expect1;
@@ -1209,14 +1221,20 @@ __global__ void k_halo_wait(const unsigned long long *flag0, unsigned long long 
         return;
     const unsigned long long v = *expect + 1;
     *expect = v;
-    const long long t0 = clock64();
+    const unsigned long long t0 = global_ns();
+    unsigned int spins = 0;
     while (true) {
         unsigned long long cur;
         asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(cur) : "l"(flag) : "memory");
         if (cur >= v)
             break;
-        if (clock64() - t0 > 20000000000LL)  // ~10 s: a lost neighbour must not hang the GPU
-            __trap();
+        if (timeout_ns && (++spins & 1023u) == 0 && global_ns() - t0 > timeout_ns) {
+            if (err) {
+                atomicOr_system(err, 1u << threadIdx.x);
+                __threadfence_system();
+            }
+            break;
+        }
     }
 }
 
@@ -1253,11 +1271,11 @@ void launch_halo_push(const HaloRun &up, const HaloRun &low, cudaStream_t st)
 
 void launch_halo_wait(const unsigned long long *flag0, unsigned long long *expect0,
                       const unsigned long long *flag1, unsigned long long *expect1,
-                      cudaStream_t st)
+                      unsigned long long timeout_ns, unsigned int *err, cudaStream_t st)
 {
     if (!flag0 && !flag1)
         return;
-    k_halo_wait<<<1, 2, 0, st>>>(flag0, expect0, flag1, expect1);
+    k_halo_wait<<<1, 2, 0, st>>>(flag0, expect0, flag1, expect1, timeout_ns, err);
     COUNT_LAUNCH();
 }
 

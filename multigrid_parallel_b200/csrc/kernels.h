@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 
 #include "geom.h"
+#include "lu_band.cuh"
 
 namespace mgb {
 
@@ -93,9 +94,11 @@ struct HaloRun {  // one direction: up to two contiguous runs (colours) + where 
 };
 // both directions in ONE launch, both waits in ONE launch
 void launch_halo_push(const HaloRun &up, const HaloRun &low, cudaStream_t st);
+// timeout_ns: give up after that long (0: never) and set bit 0 (lower neighbour) /
+// bit 1 (upper neighbour) of *err (host-mapped) instead of hanging or trapping
 void launch_halo_wait(const unsigned long long *flag0, unsigned long long *expect0,
                       const unsigned long long *flag1, unsigned long long *expect1,
-                      cudaStream_t st);
+                      unsigned long long timeout_ns, unsigned int *err, cudaStream_t st);
 
 // ---- the deep coarse levels as one single-block kernel (tail.cu) ----
 struct TailLevel {
@@ -107,8 +110,7 @@ struct TailP {
     int top;          // levels top .. 0 .. top are done in the kernel
     int gs;           // smoothing iterations per leg
     int zero_top;     // level `top` starts from a zero guess (it is a coarse level)
-    int nc;           // unknowns of level 0 (<= 1024)
-    const double *lu, *lut;
+    LuBand lu;        // factorised operator of level 0 in band form (n <= 1024)
     TailLevel lv[8];
 };
 void launch_coarse_tail(const TailP &p, cudaStream_t st);
@@ -127,11 +129,17 @@ bool launch_tile_prolong(const Geo &gc, const double *ec, const Geo &gf, double 
 // dense coarse operator + LU (mg_3d.h:147-273, gauss_elim.h:9-60)
 void launch_coarse_matrix(double *A, int ni, int nj, int nk, double h,
                           cudaStream_t st);
-void launch_lu_factor(double *a, int n, cudaStream_t st);
-void launch_transpose(const double *a, double *at, int n, cudaStream_t st);
-// x = (LU)^-1 b; lut = transpose of lu; b, x are plain dense vectors
-void launch_lu_solve(const double *lu, const double *lut, int n, const double *b,
-                     double *x, cudaStream_t st);
+// band-limited in-place factorisation of the dense n x n array `a` (half
+// bandwidth bw; bw >= n-1 = plain dense), two launches whatever n is
+void launch_lu_factor_band(double *a, int n, int bw, cudaStream_t st);
+// half bandwidth of a dense matrix (max |r-c| over its non-zeros); synchronises
+int lu_bandwidth(const double *a, int n, cudaStream_t st);
+// dense factor -> band arrays (lu_band.cuh); B.lb/ub: bw*n doubles each, B.ud: n
+void launch_lu_extract_band(const double *a, const LuBand &B, cudaStream_t st);
+// x = (LU)^-1 b in one launch: plain dense vectors, or level 0's colour-split d / u
+void launch_lu_solve_dense(const LuBand &B, const double *b, double *x, cudaStream_t st);
+void launch_lu_solve_level(const LuBand &B, const Geo &g, const double *d0, double *u0,
+                           cudaStream_t st);
 // launches issued through the wrappers above (all threads, all solvers)
 long long launches_issued();
 

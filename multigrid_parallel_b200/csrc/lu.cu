@@ -1,13 +1,25 @@
-// lu.cu -- dense coarsest-level operator on the GPU: build, factor once
-// (Doolittle, no pivoting), solve by column sweeps.
+// lu.cu -- coarsest-level operator on the GPU: build, factor once (Doolittle,
+// no pivoting), solve once per cycle -- all restricted to the BAND of the
+// operator (half bandwidth nj*nk), bit-identical to the reference's dense loops.
 //
 // Bit-exactness contract (gauss_elim.h:9-60): the factorisation updates every
 // entry with the pivots in ascending order, multiplier = a_ki * (1/a_ii); the
 // forward sum of row i runs over ascending j, the backward sum over DESCENDING
-// j, each starting from 0.  A column sweep (finish x_j, then add column j into
-// all pending row sums) performs exactly that sequence per row while exposing
-// n-way parallelism per step.
+// j, each starting from 0.
+//
+// Why the band is enough.  Without pivoting the fill of L and U stays inside
+// the band of A.  Outside it the reference computes z = (+0)*(1/a_ii) = +-0 and
+// a[k][j] -= (+-0)*a[i][j]; an entry of the trailing matrix is never -0 (it is
+// +0 from the memset or the result of a subtraction, and x - x = +0), so that
+// update changes nothing, bit for bit.  The multipliers themselves are stored:
+// out of the band they are copysign(0, 1/a_ii), which a fix-up pass writes so
+// that even the sign of zero of the dense factor (mgb_coarse_lu_download, the
+// drop-in's `A`) equals the reference's.  The solve: see lu_band.cuh.
+#include <cstdio>
+
 #include "kernels.h"
+#include "lu_band.cuh"
+#include "devmath.cuh"
 
 namespace mgb {
 
@@ -46,146 +58,174 @@ void launch_coarse_matrix(double *A, int ni, int nj, int nk, double h, cudaStrea
     ++*launch_counter();
 }
 
-// pivot p, step 1: multipliers  a[r][p] *= 1/a[p][p]   (r > p)
-__global__ void __launch_bounds__(256) k_lu_scale(double *__restrict__ a, int n, int p)
+// ----------------------------------------------------------------------------
+// factorisation, band-limited, ONE launch (gauss_elim.h:9-29)
+//
+// One block; per pivot p the window rows/columns p+1 .. min(p+bw, n-1) get
+// a[r][c] -= z_r * a[p][c] with z_r = a[r][p] * (1/a[p][p]) recomputed by every
+// thread that needs it (the same product, hence the same bits); one barrier per
+// pivot.  Column p is left UNSCALED -- nothing reads it again during the
+// factorisation -- and k_lu_finish_lower turns it into the stored multipliers.
+// ----------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) k_lu_factor_band(double *a, int n, int bw)
 {
-    const int r = p + 1 + blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= n)
-        return;
-    const double pinv = __drcp_rn(a[(long long)p * n + p]);
-    a[(long long)r * n + p] = __dmul_rn(a[(long long)r * n + p], pinv);
-}
-
-// pivot p, step 2: a[r][c] -= a[r][p]*a[p][c]   (r > p, c > p)
-__global__ void __launch_bounds__(256) k_lu_update(double *__restrict__ a, int n, int p)
-{
-    const int c = p + 1 + blockIdx.x * blockDim.x + threadIdx.x;
-    const int r = p + 1 + blockIdx.y;
-    if (c >= n)
-        return;
-    const double z = a[(long long)r * n + p];
-    const double t = __dmul_rn(z, a[(long long)p * n + c]);
-    a[(long long)r * n + c] = __dsub_rn(a[(long long)r * n + c], t);
-}
-
-void launch_lu_factor(double *a, int n, cudaStream_t st)
-{
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     for (int p = 0; p < n - 1; p++) {
-        const int rem = n - 1 - p;
-        k_lu_scale<<<(rem + 255) / 256, 256, 0, st>>>(a, n, p);
-        dim3 grid((rem + 255) / 256, rem);
-        k_lu_update<<<grid, 256, 0, st>>>(a, n, p);
-        *launch_counter() += 2;
+        const int w = min(bw, n - 1 - p);
+        const double pinv = __drcp_rn(a[(size_t)p * n + p]);  // 1./a[ni+i]
+        const double *prow = a + (size_t)p * n + p + 1;
+        for (int rr = ty; rr < w; rr += 32) {
+            double *row = a + (size_t)(p + 1 + rr) * n + p;
+            const double z = __dmul_rn(row[0], pinv);
+            for (int cc = tx; cc < w; cc += 32)
+                row[1 + cc] = __dsub_rn(row[1 + cc], __dmul_rn(z, prow[cc]));
+        }
+        __syncthreads();
     }
 }
 
-__global__ void k_transpose(const double *__restrict__ a, double *__restrict__ at, int n)
+// strictly lower triangle: multipliers inside the band, signed zeros outside
+__global__ void __launch_bounds__(256) k_lu_finish_lower(double *a, int n, int bw)
 {
-    __shared__ double tile[32][33];
-    int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 32 + threadIdx.y;
-    if (x < n && y < n)
-        tile[threadIdx.y][threadIdx.x] = a[(long long)y * n + x];
-    __syncthreads();
-    x = blockIdx.y * 32 + threadIdx.x;
-    y = blockIdx.x * 32 + threadIdx.y;
-    if (x < n && y < n)
-        at[(long long)y * n + x] = tile[threadIdx.x][threadIdx.y];
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    const int r = blockIdx.y;
+    if (c >= r || c >= n)
+        return;
+    const double pinv = __drcp_rn(a[(size_t)c * n + c]);
+    double *e = a + (size_t)r * n + c;
+    *e = r - c <= bw ? __dmul_rn(*e, pinv) : __dmul_rn(0., pinv);
 }
 
-void launch_transpose(const double *a, double *at, int n, cudaStream_t st)
+void launch_lu_factor_band(double *a, int n, int bw, cudaStream_t st)
 {
-    dim3 grid((n + 31) / 32, (n + 31) / 32), block(32, 32);
-    k_transpose<<<grid, block, 0, st>>>(a, at, n);
+    if (n < 2)
+        return;
+    if (bw > n - 1)
+        bw = n - 1;
+    if (bw < 0)
+        bw = 0;
+    k_lu_factor_band<<<1, 1024, 0, st>>>(a, n, bw);
+    k_lu_finish_lower<<<dim3((n + 255) / 256, n), 256, 0, st>>>(a, n, bw);
+    *launch_counter() += 2;
+}
+
+// half bandwidth of a dense matrix: max |r - c| over its non-zero entries
+__global__ void __launch_bounds__(256) k_lu_bandwidth(const double *__restrict__ a, int n, int *out)
+{
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    const int r = blockIdx.y;
+    int d = 0;
+    if (c < n && a[(size_t)r * n + c] != 0.)
+        d = r > c ? r - c : c - r;
+    for (int o = 16; o > 0; o >>= 1)
+        d = max(d, __shfl_down_sync(0xffffffffu, d, o));
+    if ((threadIdx.x & 31) == 0 && d > 0)
+        atomicMax(out, d);
+}
+
+int lu_bandwidth(const double *a, int n, cudaStream_t st)
+{
+    int *d_bw = nullptr, bw = n - 1;
+    if (cudaMalloc(&d_bw, sizeof(int)) != cudaSuccess)
+        return bw;
+    cudaMemsetAsync(d_bw, 0, sizeof(int), st);
+    k_lu_bandwidth<<<dim3((n + 255) / 256, n), 256, 0, st>>>(a, n, d_bw);
+    ++*launch_counter();
+    cudaMemcpyAsync(&bw, d_bw, sizeof(int), cudaMemcpyDeviceToHost, st);
+    cudaStreamSynchronize(st);
+    cudaFree(d_bw);
+    return bw;
+}
+
+// dense factor -> band arrays of lu_band.cuh
+__global__ void __launch_bounds__(256) k_lu_extract_band(const double *__restrict__ a, LuBand B)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int d = blockIdx.y;  // 0: diagonal, 1..bw: distance
+    const int n = B.n;
+    if (i >= n)
+        return;
+    if (d == 0) {
+        B.ud[i] = a[(size_t)i * n + i];
+        return;
+    }
+    B.lb[(size_t)(d - 1) * n + i] = i - d >= 0 ? a[(size_t)i * n + i - d] : 0.;
+    B.ub[(size_t)(d - 1) * n + i] = i + d < n ? a[(size_t)i * n + i + d] : 0.;
+}
+
+void launch_lu_extract_band(const double *a, const LuBand &B, cudaStream_t st)
+{
+    k_lu_extract_band<<<dim3((B.n + 255) / 256, B.bw + 1), 256, 0, st>>>(a, B);
     ++*launch_counter();
 }
 
-// One block.  Thread t owns rows t, t+B, t+2B, ... (at most RPT of them) and
-// keeps their running sums in registers; xs[] (shared) carries z, then x.
-// lut[c*n + r] = lu[r*n + c], so step c reads one contiguous row of lut.
-template <int RPT>
-__global__ void __launch_bounds__(1024)
-k_lu_solve(const double *__restrict__ lu, const double *__restrict__ lut, int n,
-           const double *__restrict__ b, double *__restrict__ x)
+// ----------------------------------------------------------------------------
+// solve (gauss_elim.h:31-60), one launch: LEVEL form reads b from / writes x to
+// the colour-split arrays of level 0 directly (the dense vectors of
+// solveWithLU(LU, n, d[0], u[0]) are their natural-layout views, mg_3d.h:1270)
+// ----------------------------------------------------------------------------
+template <bool LEVEL>
+__global__ void __launch_bounds__(32 * kLuWarps)
+k_lu_band_solve(const LuBand B, const Geo g, const double *__restrict__ rhs, double *__restrict__ x)
 {
-    extern __shared__ double xs[];
-    const int t = threadIdx.x, B = blockDim.x;
-    double sum[RPT];
-#pragma unroll
-    for (int s = 0; s < RPT; s++)
-        sum[s] = 0.;
-    // forward: L z = b, unit lower triangle, ascending columns
-    for (int c = 0; c < n; c++) {
-        if (c % B == t) {
-            const int sl = c / B;
-            double sv = 0.;
-#pragma unroll
-            for (int s = 0; s < RPT; s++)
-                if (s == sl)
-                    sv = sum[s];
-            xs[c] = __dsub_rn(b[c], sv);
+    extern __shared__ double lu_sh[];
+    const int n = B.n, npad = (n + 31) & ~31;
+    double *xs = lu_sh;
+    double *tri = xs + npad;
+    int *flags = reinterpret_cast<int *>(tri + kLuWarps * kLuTriDoubles);
+    const int t = threadIdx.x;
+    for (int i = t; i < npad; i += blockDim.x) {
+        double b = 0.;
+        if (i < n) {
+            if (LEVEL) {
+                const int k = i % g.nk, j = (i / g.nk) % g.nj, il = i / (g.nk * g.nj);
+                b = rd_split(g, rhs, il, j, k);
+            } else {
+                b = rhs[i];
+            }
         }
-        __syncthreads();
-        const double xc = xs[c];
-        const double *col = lut + (long long)c * n;
-#pragma unroll
-        for (int s = 0; s < RPT; s++) {
-            const int r = t + s * B;
-            if (r > c && r < n)
-                sum[s] = __dadd_rn(sum[s], __dmul_rn(col[r], xc));
+        xs[i] = b;
+    }
+    if (t < 2)
+        flags[t] = 0;
+    __syncthreads();
+    lu_band_solve(B, xs, tri, flags, t >> 5, t & 31);
+    __syncthreads();
+    for (int i = t; i < n; i += blockDim.x) {
+        if (LEVEL) {
+            const int k = i % g.nk, j = (i / g.nk) % g.nj, il = i / (g.nk * g.nj);
+            const int c = (g.i0 + il + j + k) & 1;
+            x[(long long)c * g.cs + ((long long)il * g.nj + j) * g.kh + (k >> 1)] = xs[i];
+        } else {
+            x[i] = xs[i];
         }
     }
-#pragma unroll
-    for (int s = 0; s < RPT; s++)
-        sum[s] = 0.;
-    __syncthreads();
-    // backward: U x = z, descending columns
-    for (int c = n - 1; c >= 0; c--) {
-        if (c % B == t) {
-            const int sl = c / B;
-            double sv = 0.;
-#pragma unroll
-            for (int s = 0; s < RPT; s++)
-                if (s == sl)
-                    sv = sum[s];
-            xs[c] = __ddiv_rn(__dsub_rn(xs[c], sv), lu[(long long)c * n + c]);
-        }
-        __syncthreads();
-        const double xc = xs[c];
-        const double *col = lut + (long long)c * n;
-#pragma unroll
-        for (int s = 0; s < RPT; s++) {
-            const int r = t + s * B;
-            if (r < c)
-                sum[s] = __dadd_rn(sum[s], __dmul_rn(col[r], xc));
-        }
-    }
-    __syncthreads();
-    for (int r = t; r < n; r += B)
-        x[r] = xs[r];
 }
 
-void launch_lu_solve(const double *lu, const double *lut, int n, const double *b,
-                     double *x, cudaStream_t st)
+template <bool LEVEL>
+static void launch_band_solve(const LuBand &B, const Geo &g, const double *rhs, double *x,
+                              cudaStream_t st)
 {
-    int B = 32;
-    while (B < n && B < 1024)
-        B *= 2;
-    const int rpt = (n + B - 1) / B;
-    const size_t sh = sizeof(double) * n;
-    if (sh > 48 * 1024) {  // opt in to large dynamic shared memory (n <= 8192)
-        cudaFuncSetAttribute(k_lu_solve<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh);
-        cudaFuncSetAttribute(k_lu_solve<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh);
-        cudaFuncSetAttribute(k_lu_solve<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh);
+    const size_t sh = sizeof(double) * lu_solve_smem_doubles(B.n);
+    static size_t allowed = 48 * 1024;
+    if (sh > allowed) {
+        cudaFuncSetAttribute(k_lu_band_solve<LEVEL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)sh);
+        allowed = sh;
     }
-    if (rpt <= 1)
-        k_lu_solve<1><<<1, B, sh, st>>>(lu, lut, n, b, x);
-    else if (rpt <= 2)
-        k_lu_solve<2><<<1, B, sh, st>>>(lu, lut, n, b, x);
-    else if (rpt <= 4)
-        k_lu_solve<4><<<1, B, sh, st>>>(lu, lut, n, b, x);
-    else
-        k_lu_solve<8><<<1, B, sh, st>>>(lu, lut, n, b, x);
+    k_lu_band_solve<LEVEL><<<1, 32 * kLuWarps, sh, st>>>(B, g, rhs, x);
     ++*launch_counter();
+}
+
+void launch_lu_solve_dense(const LuBand &B, const double *b, double *x, cudaStream_t st)
+{
+    launch_band_solve<false>(B, Geo{}, b, x, st);
+}
+
+void launch_lu_solve_level(const LuBand &B, const Geo &g, const double *d0, double *u0,
+                           cudaStream_t st)
+{
+    launch_band_solve<true>(B, g, d0, u0, st);
 }
 
 }  // namespace mgb

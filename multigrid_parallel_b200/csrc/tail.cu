@@ -158,43 +158,33 @@ __device__ void t_prolong(const TailLevel &C, const TailLevel &F)
     }
 }
 
-// solveWithLU on level 0 (gauss_elim.h:31-60): L z = b ascending, U x = z
-// descending, every row sum in the reference's column order.  n <= 1024:
-// thread t owns row t; xs[] carries z, then x.
-__device__ void t_coarse_solve(const TailLevel &L, const double *__restrict__ lu,
-                               const double *__restrict__ lut, int n, double *xs)
+// solveWithLU on level 0 (gauss_elim.h:31-60) through the warp-cooperative
+// band solve of lu_band.cuh; the dense vectors are the natural-layout views of
+// level 0 (mg_3d.h:1270)
+__device__ void t_coarse_solve(const TailLevel &L, const LuBand &B, double *sh)
 {
     const Geo &g = L.g;
+    const int n = B.n, npad = (n + 31) & ~31;
+    double *xs = sh;
+    double *tri = xs + npad;
+    int *flags = reinterpret_cast<int *>(tri + kLuWarps * kLuTriDoubles);
     const int t = threadIdx.x;
-    double bt = 0.;
-    int bi = 0, bj = 0, bk = 0;
-    if (t < n) {  // the dense vectors are the natural-layout views of level 0
-        bk = t % g.nk;
-        bj = (t / g.nk) % g.nj;
-        bi = t / (g.nk * g.nj);
-        bt = rd_split(g, L.d, bi, bj, bk);
+    for (int i = t; i < npad; i += kTailThreads) {
+        double b = 0.;
+        if (i < n)
+            b = rd_split(g, L.d, i / (g.nk * g.nj), (i / g.nk) % g.nj, i % g.nk);
+        xs[i] = b;
     }
-    double sum = 0.;
-    for (int c = 0; c < n; c++) {
-        if (t == c)
-            xs[c] = __dsub_rn(bt, sum);
-        __syncthreads();
-        if (t > c && t < n)
-            sum = __dadd_rn(sum, __dmul_rn(lut[(long long)c * n + t], xs[c]));
-    }
-    sum = 0.;
+    if (t < 2)
+        flags[t] = 0;
     __syncthreads();
-    for (int c = n - 1; c >= 0; c--) {
-        if (t == c)
-            xs[c] = __ddiv_rn(__dsub_rn(xs[c], sum), lu[(long long)c * n + c]);
-        __syncthreads();
-        if (t < c)
-            sum = __dadd_rn(sum, __dmul_rn(lut[(long long)c * n + t], xs[c]));
-    }
+    if (t < 32 * kLuWarps)
+        lu_band_solve(B, xs, tri, flags, t >> 5, t & 31);
     __syncthreads();
-    if (t < n) {
+    for (int i = t; i < n; i += kTailThreads) {
+        const int bk = i % g.nk, bj = (i / g.nk) % g.nj, bi = i / (g.nk * g.nj);
         const int col = (bi + bj + bk) & 1;
-        L.u[(long long)col * g.cs + ((long long)bi * g.nj + bj) * g.kh + (bk >> 1)] = xs[t];
+        L.u[(long long)col * g.cs + ((long long)bi * g.nj + bj) * g.kh + (bk >> 1)] = xs[i];
     }
 }
 
@@ -207,7 +197,7 @@ __device__ void t_zero(const TailLevel &L)
 
 __global__ void __launch_bounds__(kTailThreads) k_coarse_tail(const TailP P)
 {
-    __shared__ double xs[1024];
+    extern __shared__ double tail_sh[];
     // down (mg_3d.h:1254-1318)
     for (int q = P.top; q >= 1; q--) {
         const TailLevel &L = P.lv[q];
@@ -231,7 +221,7 @@ __global__ void __launch_bounds__(kTailThreads) k_coarse_tail(const TailP P)
         t_zero(P.lv[0]);
         __syncthreads();
     }
-    t_coarse_solve(P.lv[0], P.lu, P.lut, P.nc, xs);
+    t_coarse_solve(P.lv[0], P.lu, tail_sh);
     __syncthreads();
     // up (1331-1351)
     for (int q = 1; q <= P.top; q++) {
@@ -251,7 +241,9 @@ __global__ void __launch_bounds__(kTailThreads) k_coarse_tail(const TailP P)
 
 void launch_coarse_tail(const TailP &p, cudaStream_t st)
 {
-    k_coarse_tail<<<1, kTailThreads, 0, st>>>(p);
+    // n <= 1024: at most 8 KB of xs + the triangle tiles, under the 48 KB default
+    const size_t sh = sizeof(double) * lu_solve_smem_doubles(p.lu.n);
+    k_coarse_tail<<<1, kTailThreads, sh, st>>>(p);
     ++*launch_counter();
 }
 

@@ -182,6 +182,12 @@ class Solver:
         check(self.L.mgb_coarse_lu_download(self.h_, a.ctypes.data))
         return a
 
+    def coarse_info(self):
+        """(n, half bandwidth, seconds the build + factorisation took at create)"""
+        n, bw, t = C.c_int(), C.c_int(), C.c_double()
+        check(self.L.mgb_coarse_info(self.h_, n, bw, t))
+        return n.value, bw.value, t.value
+
     # -- cycles ------------------------------------------------------------
     def vcycle(self):
         """one V-cycle; returns the residual 2-norm (SolverLinSolve)"""

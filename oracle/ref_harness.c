@@ -128,6 +128,36 @@ double ref_vcycle(void)
     return r;
 }
 
+/* `n` V-cycles inside the driver's own timed region (test_mg_3d.c:36-68): ONE
+ * parallel region around the loop, barrier + single per cycle, omp_get_wtime
+ * on both sides.  Returns the seconds; *last_norm = norm after the last cycle */
+double ref_timed_cycles(int n, double *last_norm)
+{
+    int nt = omp_get_max_threads();
+    double *part = calloc(nt, sizeof(double));
+    double norm = 0;
+    int done = 0;
+    double t0 = omp_get_wtime();
+#pragma omp parallel
+    {
+        int tid = omp_get_thread_num();
+        while (done < n) {
+            part[tid] = SolverLinSolve();
+#pragma omp barrier
+#pragma omp single
+            {
+                norm = team_norm(part, nt);
+                done++;
+            }
+        }
+    }
+    double t1 = omp_get_wtime();
+    free(part);
+    if (last_norm)
+        *last_norm = norm;
+    return t1 - t0;
+}
+
 /* test_mg_3d.c:17-67; history[c] = norm after cycle c+1; returns cycles */
 int ref_solve(int coarse, int levels, int gs, double tol, int max_cycles,
               double *history, double *init_norm, double *u_out,

@@ -203,19 +203,47 @@ def test_prolong_correct_bitwise(mgb, orc, coarse, levels):
             assert np.array_equal(s.download(lvl, mgb.MGB_U), ef), f"level {lvl}"
 
 
-@pytest.mark.parametrize("coarse", [(3, 3, 3), (5, 5, 5), (3, 5, 9), (9, 9, 9)])
+def _bits(a):
+    return np.ascontiguousarray(a, dtype=np.float64).view(np.uint64)
+
+
+# (17, 9, 9) = the coarsest grid of BASELINE config 5 on 8 GPUs: 1377 unknowns
+@pytest.mark.parametrize("coarse", [(3, 3, 3), (5, 5, 5), (3, 5, 9), (9, 9, 9), (3, 9, 9),
+                                    (17, 9, 9)])
 def test_coarse_lu_bitwise(mgb, orc, coarse):
+    """band-limited factor + warp-cooperative band solve (csrc/lu.cu, lu_band.cuh)
+    against the oracle's dense loops (gauss_elim.h:9-60): the factor down to the
+    sign of its zeros, the solution bit for bit"""
     levels = 2
     with _mk(mgb, coarse, levels) as s:
         hc = s.spacing(0)
         A = orc.coarse_matrix(coarse, hc)
         orc.lu_factor(A)
-        assert np.array_equal(s.coarse_lu(), A)
-        b = seeded(coarse, 13)
-        s.upload(0, mgb.MGB_D, b)
-        s.coarse_solve()
-        want = orc.lu_solve(A, b.reshape(-1)).reshape(coarse)
-        assert np.array_equal(s.download(0, mgb.MGB_U), want)
+        n, bw, secs = s.coarse_info()
+        assert n == int(np.prod(coarse)) and bw == min(coarse[1] * coarse[2], n - 1) and secs > 0
+        assert np.array_equal(_bits(s.coarse_lu()), _bits(A))
+        for seed in (13, 14):
+            b = seeded(coarse, seed)
+            s.upload(0, mgb.MGB_D, b)
+            s.coarse_solve()
+            want = orc.lu_solve(A, b.reshape(-1)).reshape(coarse)
+            assert np.array_equal(_bits(s.download(0, mgb.MGB_U)), _bits(want))
+
+
+@pytest.mark.parametrize("n,bw", [(3, 1), (40, 39), (150, 70), (257, 5)])
+def test_host_lu_generic_matrix(mgb, orc, n, bw):
+    """convertToLU_InPlace / solveWithLU on caller-owned matrices (test_lu.c flow):
+    any band structure, n not a multiple of the 32-row blocks"""
+    A = seeded((n, n), 41)
+    r, c = np.meshgrid(np.arange(n), np.arange(n), indexing="ij")
+    A[np.abs(r - c) > bw] = 0.0
+    A[np.arange(n), np.arange(n)] = -(np.abs(np.diag(A)) + 2.0 * bw)
+    want = A.copy()
+    orc.lu_factor(want)
+    mgb.host_lu_factor(A)
+    assert np.array_equal(_bits(A), _bits(want))
+    b = seeded((n,), 42)
+    assert np.array_equal(_bits(mgb.host_lu_solve(A, b)), _bits(orc.lu_solve(want, b)))
 
 
 def test_known_answer_lu(mgb):
