@@ -91,9 +91,27 @@ int mgb_sync(mgb_solver *s);
  * `host` is natural layout, ni*nj*nk doubles; pinned or pageable. */
 int mgb_upload(mgb_solver *s, int level, int which, const double *host);
 int mgb_download(mgb_solver *s, int level, int which, double *host);
+/* the same for a contiguous run of the natural layout: doubles [first, first+count)
+ * of the local planes; `host` points at the first of them */
+int mgb_upload_range(mgb_solver *s, int level, int which, long long first, long long count,
+                     const double *host);
+int mgb_download_range(mgb_solver *s, int level, int which, long long first, long long count,
+                       double *host);
 int mgb_zero(mgb_solver *s, int level, int which);
 /* setupBoundaryConditions (mg_3d.h:1147-1239) on the device array */
 int mgb_set_dirichlet(mgb_solver *s, int level, int which);
+/* updateEdgeValues (mg_3d.h:304-430; SolverSmoothenEdgeValues, 1422-1423): inner
+ * points of the 12 edges = mean of their two inward neighbours, then the 8 corners
+ * = mean of their three edge neighbours.  Unpartitioned levels only. */
+int mgb_edge_values(mgb_solver *s, int level, int which);
+/* single-grid sessions (levels == 1, the raw-pointer API preSmoother / postSmoother /
+ * calculateResidual(v, d, N, h, ..) of test_rb_gs_3d.c:56-101): the caller's spacing */
+int mgb_set_spacing(mgb_solver *s, double h);
+/* page-lock a host range the caller owns (cudaHostRegister) so that mgb_upload /
+ * mgb_download run at the pinned PCIe rate; the drop-in headers do this for the
+ * finest-level grid / rhs arrays they hand out (SolverGetDetails, mg_3d.h:275-293) */
+int mgb_pin_host(void *p, unsigned long long bytes);
+int mgb_unpin_host(void *p);
 /* GetL2NormOfVector (mg_3d.h:783-792): sum of squares over ALL points */
 int mgb_sumsq(mgb_solver *s, int level, int which, double *sumsq);
 /* test_mg_3d.c:78-97: sum over all points of (u - BCFunc)^2 at the finest level */
@@ -142,6 +160,18 @@ int mgb_coarse_info(const mgb_solver *s, int *n, int *half_bandwidth, double *fa
  * mgb_solve = the driver loop test_mg_3d.c:40-66: cycle while
  * sqrt(sumsq) > threshold; history[c] = norm after cycle c+1. */
 int mgb_vcycle(mgb_solver *s, double *sumsq);
+/* mgb_fmg_init = SolverFMGInitialize (mg_3d.h:1364-1404; upstream keeps it
+ * commented out, the live copy mg_dirichlet_analytic.c:771-806 predates today's
+ * vcycle signature): coarsest LU solve, then per level interpolate the coarser
+ * solution, impose the boundary values, zero the coarser level, one V-cycle
+ * entered at that level.  Exactly those statements in that order -- including
+ * their quirks: the LU solve overwrites the boundary values put into u[0], and a
+ * V-cycle entered below the finest level zeroes its entry level first
+ * (mg_3d.h:1254-1260) -- so every level's u and d equal the reference's bit for
+ * bit (tests/golden/fmg.json).  *sumsq = squared residual norm after the last
+ * (finest-level) cycle.  Call it where mg_dirichlet_analytic.c:984-989 does:
+ * after the boundary values are in place, before the V-cycle loop. */
+int mgb_fmg_init(mgb_solver *s, double *sumsq);
 int mgb_solve(mgb_solver *s, double threshold, int max_cycles,
               double *history, int *cycles);
 

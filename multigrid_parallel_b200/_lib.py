@@ -59,9 +59,15 @@ def load_library():
     L.mgb_tile_plan.argtypes = [i, i, i, i, C.POINTER(C.c_longlong)]
     L.mgb_upload.argtypes = [vp, i, i, C.c_void_p]
     L.mgb_download.argtypes = [vp, i, i, C.c_void_p]
+    L.mgb_upload_range.argtypes = [vp, i, i, C.c_longlong, C.c_longlong, C.c_void_p]
+    L.mgb_download_range.argtypes = [vp, i, i, C.c_longlong, C.c_longlong, C.c_void_p]
     L.mgb_zero.argtypes = [vp, i, i]
     L.mgb_set_dirichlet.argtypes = [vp, i, i]
     L.mgb_sumsq.argtypes = [vp, i, i, c_dp]
+    L.mgb_edge_values.argtypes = [vp, i, i]
+    L.mgb_set_spacing.argtypes = [vp, d]
+    L.mgb_pin_host.argtypes = [C.c_void_p, C.c_ulonglong]
+    L.mgb_unpin_host.argtypes = [C.c_void_p]
     L.mgb_error_sumsq.argtypes = [vp, c_dp]
     L.mgb_half_sweep.argtypes = [vp, i, i]
     L.mgb_smooth.argtypes = [vp, i, i, i]
@@ -75,6 +81,7 @@ def load_library():
     L.mgb_coarse_lu_download.argtypes = [vp, C.c_void_p]
     L.mgb_coarse_info.argtypes = [vp, c_ip, c_ip, c_dp]
     L.mgb_vcycle.argtypes = [vp, c_dp]
+    L.mgb_fmg_init.argtypes = [vp, c_dp]
     L.mgb_solve.argtypes = [vp, d, i, c_dp, c_ip]
     L.mgb_timing.argtypes = [vp, i, i, c_ip, c_dp]
     L.mgb_timing_reset.argtypes = [vp]

@@ -14,6 +14,8 @@
 
 #include "mgb.h"
 
+#ifndef MGB_COMPAT_CHECK_DEFINED
+#define MGB_COMPAT_CHECK_DEFINED
 static void mgb_compat_check(int rc, const char *what)
 {
     if (rc != 0) {
@@ -22,6 +24,7 @@ static void mgb_compat_check(int rc, const char *what)
         abort();
     }
 }
+#endif
 
 /* reference gauss_elim.h:9-29 */
 void convertToLU_InPlace(double *a, int n)

@@ -33,18 +33,16 @@
 #include <assert.h>
 #include <limits.h>
 #include <math.h>
-#include <signal.h>
 #include <stdbool.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
-#include <sys/mman.h>
-#include <unistd.h>
 
 #include <omp.h>
 
 #include "mgb.h"
+#include "mgb_coherence.h"
 
 #include "gauss_elim.h"
 #include "timing_info.h"
@@ -61,124 +59,27 @@ double spacing;
 
 /* ---- private state of the GPU backend ---- */
 static mgb_solver *mgGpu = NULL;
-static int mgLazySync = 1;
+static int mgDevice = 0;
+static MgArr *mgU = NULL, *mgD = NULL; /* finest-level grid / rhs (SolverGetDetails) */
 
-enum { MG_CLEAN = 0, MG_HOST_NEWER = 1, MG_DEV_NEWER = 2 };
-typedef struct {
-    double *host;
-    size_t bytes;  /* page-rounded */
-    int which;     /* MGB_U / MGB_D */
-    volatile int state;
-    volatile int prot; /* current PROT_* of the host pages */
-} MgMirror;
-static MgMirror mgMirror[2];
-static volatile int mgMirrorLock = 0;
-static struct sigaction mgOldSegv;
-static int mgSegvInstalled = 0;
+/* second mappings of the arrays allocGridLevels hands out (finest levels only) */
+enum { MG_MAX_ALIAS = 8 };
+static struct { double *view; char *alias; size_t bytes; } mgAliasTab[MG_MAX_ALIAS];
 
-#define MGB_OK(call) mgb_compat_check((call), #call)
-
-static size_t mgPageRound(size_t n)
+static char *mgAliasOf(const double *view)
 {
-    const size_t pg = (size_t)sysconf(_SC_PAGESIZE);
-    return (n + pg - 1) / pg * pg;
-}
-
-static void mgProtect(MgMirror *m, int prot)
-{
-    if (!mgLazySync || !m->host || m->prot == prot)
-        return;
-    mprotect(m->host, m->bytes, prot);
-    m->prot = prot;
-}
-
-/* bring the host copy up to date (device -> host) */
-static void mgPull(MgMirror *m)
-{
-    if (m->state != MG_DEV_NEWER)
-        return;
-    mgProtect(m, PROT_READ | PROT_WRITE);
-    MGB_OK(mgb_download(mgGpu, numLevels - 1, m->which, m->host));
-    /* lazy mode: a later host write faults once and marks the pages dirty;
-     * explicit mode cannot see host writes, so assume one happens */
-    m->state = mgLazySync ? MG_CLEAN : MG_HOST_NEWER;
-    mgProtect(m, PROT_READ);
-}
-
-/* bring the device copy up to date (host -> device) */
-static void mgPush(MgMirror *m)
-{
-    if (m->state != MG_HOST_NEWER)
-        return;
-    MGB_OK(mgb_upload(mgGpu, numLevels - 1, m->which, m->host));
-    m->state = MG_CLEAN;
-    mgProtect(m, PROT_READ);
-}
-
-static void mgSegvHandler(int sig, siginfo_t *si, void *ctx)
-{
-    const uintptr_t a = (uintptr_t)si->si_addr;
-    for (int t = 0; t < 2; t++) {
-        MgMirror *m = &mgMirror[t];
-        if (!m->host || a < (uintptr_t)m->host || a >= (uintptr_t)m->host + m->bytes)
-            continue;
-        while (__atomic_test_and_set(&mgMirrorLock, __ATOMIC_ACQUIRE))
-            ;
-        if (m->prot == PROT_NONE) {
-            mgPull(m); /* first touch after GPU work */
-        } else if (m->prot == PROT_READ) {
-            m->state = MG_HOST_NEWER; /* first host write since the last sync */
-            mgProtect(m, PROT_READ | PROT_WRITE);
-        }
-        __atomic_clear(&mgMirrorLock, __ATOMIC_RELEASE);
-        return; /* retry the faulting access */
-    }
-    /* not ours: hand over to whoever was installed before */
-    sigaction(SIGSEGV, &mgOldSegv, NULL);
-    (void)sig;
-    (void)ctx;
-}
-
-static void mgInstallSegv(void)
-{
-    if (!mgLazySync || mgSegvInstalled)
-        return;
-    struct sigaction sa;
-    memset(&sa, 0, sizeof sa);
-    sa.sa_sigaction = mgSegvHandler;
-    sa.sa_flags = SA_SIGINFO | SA_NODEFER;
-    sigemptyset(&sa.sa_mask);
-    sigaction(SIGSEGV, &sa, &mgOldSegv);
-    mgSegvInstalled = 1;
-}
-
-static MgMirror *mgMirrorOf(const double *p)
-{
-    for (int t = 0; t < 2; t++)
-        if (mgMirror[t].host && mgMirror[t].host == p)
-            return &mgMirror[t];
+    for (int t = 0; t < MG_MAX_ALIAS; t++)
+        if (mgAliasTab[t].view == view)
+            return mgAliasTab[t].alias;
     return NULL;
 }
 
 /* explicit-mode bookkeeping: the host may have written p */
 static void mgTouchedByHost(const double *p)
 {
-    MgMirror *m = mgMirrorOf(p);
-    if (m && !mgLazySync)
+    MgArr *m = mgArrOf(p);
+    if (m && !m->lazy)
         m->state = MG_HOST_NEWER;
-}
-
-static void mgSyncToDevice(void)
-{
-    mgPush(&mgMirror[0]);
-    mgPush(&mgMirror[1]);
-}
-
-static void mgDeviceChangedSolution(void)
-{
-    MgMirror *m = &mgMirror[0];
-    m->state = MG_DEV_NEWER;
-    mgProtect(m, PROT_NONE);
 }
 
 static void mgPullTimings(void)
@@ -200,9 +101,24 @@ void allocGridLevels(double ***arr, const int numLevels, const int N)
     *arr = (double **)malloc(sizeof(double *) * numLevels);
     assert(*arr);
     for (int l = 0; l < numLevels; l++) {
-        /* zero-filled, page-aligned, committed lazily */
-        void *p = mmap(NULL, mgLevelBytes(l, N), PROT_READ | PROT_WRITE,
-                       MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+        /* zero-filled, page-aligned, committed lazily; the finest level -- the one the
+         * caller gets raw pointers to -- is mapped twice (mgb_coherence.h) */
+        const size_t bytes = mgLevelBytes(l, N);
+        if (l == numLevels - 1) {
+            char *alias = NULL;
+            mgMapTwice(bytes, &(*arr)[l], &alias);
+            for (int t = 0; t < MG_MAX_ALIAS && alias; t++)
+                if (!mgAliasTab[t].view) {
+                    mgAliasTab[t].view = (*arr)[l];
+                    mgAliasTab[t].alias = alias;
+                    mgAliasTab[t].bytes = bytes;
+                    alias = NULL;
+                }
+            if (alias) /* table full: do without the second mapping */
+                munmap(alias, bytes);
+            continue;
+        }
+        void *p = mmap(NULL, bytes, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
         assert(p != MAP_FAILED);
         (*arr)[l] = (double *)p;
     }
@@ -210,8 +126,15 @@ void allocGridLevels(double ***arr, const int numLevels, const int N)
 
 void deAllocGridLevels(double ***arr, const int numLevels)
 {
-    for (int l = 0; l < numLevels; l++)
+    for (int l = 0; l < numLevels; l++) {
+        for (int t = 0; t < MG_MAX_ALIAS; t++)
+            if (mgAliasTab[t].view == (*arr)[l]) {
+                munmap(mgAliasTab[t].alias, mgAliasTab[t].bytes);
+                mgAliasTab[t].view = NULL;
+                mgAliasTab[t].alias = NULL;
+            }
         munmap((*arr)[l], mgLevelBytes(l, coarseGridNum));
+    }
     free(*arr);
 }
 
@@ -260,7 +183,7 @@ void SolverInitialize(int argc, char **argv)
 
     const char *e;
     mgLazySync = (e = getenv("MGB_LAZY_SYNC")) ? atoi(e) != 0 : 1;
-    const int device = (e = getenv("MGB_DEVICE")) ? atoi(e) : 0;
+    mgDevice = (e = getenv("MGB_DEVICE")) ? atoi(e) : 0;
     const int profile = (e = getenv("MGB_PROFILE")) ? atoi(e) != 0 : 1;
 
     u = NULL; d = NULL; r = NULL;
@@ -279,24 +202,29 @@ void SolverInitialize(int argc, char **argv)
 
     /* the GPU hierarchy: levels in HBM, coarse operator built + factorised there */
     MGB_OK(mgb_create(&mgGpu, coarseGridNum, coarseGridNum, coarseGridNum, numLevels,
-                      gsIterNum, device));
+                      gsIterNum, mgDevice));
     MGB_OK(mgb_set_option(mgGpu, MGB_OPT_PROFILE, profile));
+    mgCoherenceInit();
     const int top = numLevels - 1;
-    const size_t bytes = mgLevelBytes(top, coarseGridNum);
-    mgMirror[0] = (MgMirror){u[top], bytes, MGB_U, MG_CLEAN, PROT_READ | PROT_WRITE};
-    mgMirror[1] = (MgMirror){d[top], bytes, MGB_D, MG_CLEAN, PROT_READ | PROT_WRITE};
-    mgInstallSegv();
-    /* device arrays start zeroed like the calloc'd host arrays: in sync; from
-     * now on the first host write to either array is noticed */
-    mgProtect(&mgMirror[0], PROT_READ);
-    mgProtect(&mgMirror[1], PROT_READ);
+    const size_t n3 = (size_t)finestOneSideNum * finestOneSideNum * finestOneSideNum;
+    /* device arrays start zeroed like the calloc'd host arrays: in sync; from now on the
+     * first host write to either array is noticed */
+    mgU = mgArrRegister(u[top], n3 * sizeof(double), mgAliasOf(u[top]), 1, mgGpu, top, MGB_U,
+                        MG_CLEAN);
+    mgD = mgArrRegister(d[top], n3 * sizeof(double), mgAliasOf(d[top]), 1, mgGpu, top, MGB_D,
+                        MG_CLEAN);
+    assert(mgU && mgD);
+    mgSetProt(mgU, PROT_READ);
+    mgSetProt(mgD, PROT_READ);
 }
 
 /* coarsest operator (reference mg_3d.h:147-273), assembled on the GPU */
 void constructCoarseMatrixA(double *A, int N, const double h)
 {
     assert((long long)N * N * N * N * N * N < INT_MAX);
+    MG_LOCK();
     MGB_OK(mgb_host_coarse_matrix(A, N, N, N, h));
+    MG_UNLOCK();
 }
 
 /* reference mg_3d.h:275-293 */
@@ -309,9 +237,11 @@ int SolverGetDetails(double **grid, double **rhs, double *h)
     const size_t matDim = (size_t)coarseGridNum * coarseGridNum * coarseGridNum;
     A = (double *)calloc(matDim * matDim, sizeof(double));
     assert(A);
+    MG_LOCK();
     MGB_OK(mgb_coarse_lu_download(mgGpu, A));
+    MG_UNLOCK();
     if (!mgLazySync)
-        mgMirror[0].state = mgMirror[1].state = MG_HOST_NEWER;
+        mgU->state = mgD->state = MG_HOST_NEWER;
     *h = spacing;
     return finestOneSideNum;
 }
@@ -340,25 +270,140 @@ void SolverSetupBoundaryConditions()
 }
 
 /* ---- raw-pointer operators: collective over the OpenMP team, run once ----
- * The arrays of the solver's finest level are operated on in place on the
- * device; any other pointers go through the stateless staging entry points. */
+ * Three homes for the arrays:
+ *   - the solver's finest level (grid / rhs of SolverGetDetails): in place on the device;
+ *   - any other large array pair (v, d) -- test_rb_gs_3d.c:56-101 calls preSmoother /
+ *     postSmoother / calculateResidual on its own calloc'd arrays hundreds of times --
+ *     gets a SESSION: a single-grid device copy that stays resident between calls, kept
+ *     coherent with the caller's memory by page protection (mgb_coherence.h).  The host
+ *     pointer -> session registry is what SURVEY 8(b) asks for;
+ *   - everything else (small arrays, MGB_LAZY_SYNC=0): staged host -> device -> host
+ *     per call through the stateless mgb_host_* entry points. */
 static int mgIsFinest(const double *v, const double *dd, int N)
 {
     return mgGpu && N == finestOneSideNum && v == u[numLevels - 1] && dd == d[numLevels - 1];
+}
+
+enum { MG_MAX_SESSIONS = 3 };
+typedef struct {
+    mgb_solver *gpu;
+    int N;
+    double h;
+    MgArr *v, *d;
+    unsigned long stamp;
+} MgSession;
+static MgSession mgSessions[MG_MAX_SESSIONS];
+static unsigned long mgSessionClock = 0;
+
+static void mgSessionClose(MgSession *ses, int sync_host)
+{
+    if (!ses->gpu)
+        return;
+    mgArrRelease(ses->v, sync_host);
+    mgArrRelease(ses->d, 0);
+    MGB_OK(mgb_destroy(ses->gpu));
+    memset(ses, 0, sizeof *ses);
+}
+
+/* mgGpuLock held.  NULL: use the staged path */
+static MgSession *mgSessionFor(double *v, const double *dd, int N, double h)
+{
+    static long long min_bytes = -1;
+    if (min_bytes < 0) {
+        const char *e = getenv("MGB_REGISTRY_MIN_BYTES");
+        min_bytes = e ? atoll(e) : (1LL << 20);
+    }
+    const size_t bytes = (size_t)N * N * N * sizeof(double);
+    if (!mgLazySync || (long long)bytes < min_bytes || v == dd)
+        return NULL;
+    MgSession *ses = NULL, *spare = NULL;
+    for (int t = 0; t < MG_MAX_SESSIONS; t++) {
+        MgSession *c = &mgSessions[t];
+        if (c->gpu && c->v->host == v && c->d->host == dd && c->N == N)
+            ses = c;
+        else if (!c->gpu && !spare)
+            spare = c;
+    }
+    if (ses && !(mgStillProtected(ses->v) && mgStillProtected(ses->d))) {
+        /* the caller freed the arrays and got the same addresses back: start over */
+        ses->v->prot = ses->d->prot = PROT_READ | PROT_WRITE;
+        mgSessionClose(ses, 0);
+        spare = ses;
+        ses = NULL;
+    }
+    if (!ses) {
+        if (!spare) { /* evict the least recently used one (its v goes back to the host) */
+            spare = &mgSessions[0];
+            for (int t = 1; t < MG_MAX_SESSIONS; t++)
+                if (mgSessions[t].stamp < spare->stamp)
+                    spare = &mgSessions[t];
+            mgSessionClose(spare, 1);
+        }
+        ses = spare;
+        MGB_OK(mgb_create(&ses->gpu, N, N, N, 1, 1, mgDevice));
+        ses->N = N;
+        ses->h = 0.;
+        ses->v = mgArrRegister(v, bytes, NULL, 0, ses->gpu, 0, MGB_U, MG_HOST_NEWER);
+        ses->d = mgArrRegister((double *)dd, bytes, NULL, 0, ses->gpu, 0, MGB_D, MG_HOST_NEWER);
+        if (!ses->v || !ses->d || !ses->v->lazy || !ses->d->lazy) {
+            mgSessionClose(ses, 0); /* cannot be watched: staged path */
+            return NULL;
+        }
+    }
+    if (ses->h != h) {
+        MGB_OK(mgb_set_spacing(ses->gpu, h));
+        ses->h = h;
+    }
+    ses->stamp = ++mgSessionClock;
+    return ses;
+}
+
+/* a host pointer libmgb may READ from right now (mgGpuLock held): registered arrays are
+ * brought up to date first and read through their always-accessible mapping */
+static const double *mgReadable(const double *p)
+{
+    MgArr *m = mgArrOf(p);
+    if (!m)
+        return p;
+    mgArrPull(m);
+    return mgXfer(m);
+}
+
+/* ... and may WRITE to: the host copy becomes the newer one */
+static double *mgWritable(double *p)
+{
+    MgArr *m = mgArrOf(p);
+    if (!m)
+        return p;
+    mgArrPull(m);
+    m->state = MG_HOST_NEWER;
+    mgSetProt(m, PROT_READ | PROT_WRITE);
+    return mgXfer(m);
 }
 
 static void mgSmooth(double *v, const double *dd, int N, double h, int iters, int firstRed)
 {
 #pragma omp single
     {
+        MG_LOCK();
+        MgSession *ses;
         if (mgIsFinest(v, dd, N) && h == spacing) {
-            mgSyncToDevice();
+            mgArrToDevice(mgU);
+            mgArrToDevice(mgD);
             MGB_OK(mgb_smooth(mgGpu, numLevels - 1, iters, firstRed));
             MGB_OK(mgb_sync(mgGpu));
-            mgDeviceChangedSolution();
+            mgArrDeviceWrote(mgU);
+        } else if ((ses = mgSessionFor(v, dd, N, h)) != NULL) {
+            mgArrToDevice(ses->v);
+            mgArrToDevice(ses->d);
+            MGB_OK(mgb_smooth(ses->gpu, 0, iters, firstRed));
+            MGB_OK(mgb_sync(ses->gpu));
+            mgArrDeviceWrote(ses->v);
         } else {
-            MGB_OK(mgb_host_smooth(v, dd, N, N, N, h, iters, firstRed));
+            const double *dr = mgReadable(dd);
+            MGB_OK(mgb_host_smooth(mgWritable(v), dr, N, N, N, h, iters, firstRed));
         }
+        MG_UNLOCK();
     }
 }
 
@@ -376,29 +421,47 @@ void postSmoother(double *__restrict__ v, const double *__restrict__ d, const in
     mgSmooth(v, d, N, h, smootherIter, 0);
 }
 
+/* result of the last `omp single` section and who ran it.  The barrier after the read
+ * keeps a fast thread from entering the NEXT single (and overwriting both) before a
+ * slow one has looked: exactly one thread returns the value, the others 0, so the
+ * driver's sqrt(sum of squares of the partials) is unchanged (test_mg_3d.c:45-59). */
 static double mgSingleResult;
 static int mgSingleOwner;
+static double mgSingleReturn(void)
+{
+    const double ret = omp_get_thread_num() == mgSingleOwner ? mgSingleResult : 0.;
+#pragma omp barrier
+    return ret;
+}
 
-/* reference mg_3d.h:794-842: exactly one thread of the team returns the norm,
- * the others 0, so sqrt(sum of squares of the partials) is unchanged */
+/* reference mg_3d.h:794-842 */
 double calculateResidual(const double *__restrict__ v, const double *__restrict__ d,
                          const int N, const double h, double *res)
 {
 #pragma omp single
     {
         double ss = 0.;
+        MG_LOCK();
+        MgSession *ses;
         if (mgIsFinest(v, d, N) && h == spacing && (res == NULL || res == r[numLevels - 1])) {
-            mgSyncToDevice();
+            mgArrToDevice(mgU);
+            mgArrToDevice(mgD);
             MGB_OK(mgb_residual(mgGpu, numLevels - 1, res != NULL, &ss));
             if (res)
                 MGB_OK(mgb_download(mgGpu, numLevels - 1, MGB_R, res));
+        } else if (res == NULL && (ses = mgSessionFor((double *)v, d, N, h)) != NULL) {
+            mgArrToDevice(ses->v);
+            mgArrToDevice(ses->d);
+            MGB_OK(mgb_residual(ses->gpu, 0, 0, &ss));
         } else {
-            MGB_OK(mgb_host_residual(v, d, N, N, N, h, res, &ss));
+            const double *vr = mgReadable(v), *dr = mgReadable(d);
+            MGB_OK(mgb_host_residual(vr, dr, N, N, N, h, res ? mgWritable(res) : NULL, &ss));
         }
+        MG_UNLOCK();
         mgSingleResult = sqrt(ss);
         mgSingleOwner = omp_get_thread_num();
     }
-    return omp_get_thread_num() == mgSingleOwner ? mgSingleResult : 0.;
+    return mgSingleReturn();
 }
 
 double GetL2NormOfVector(const double *v, const int n)
@@ -416,7 +479,12 @@ void restrictResidual(const double *__restrict__ rf, const int Nf, double *__res
                       const int Nc)
 {
 #pragma omp single
-    MGB_OK(mgb_host_restrict(rf, Nf, Nf, Nf, dc, Nc, Nc, Nc));
+    {
+        MG_LOCK();
+        const double *rr = mgReadable(rf);
+        MGB_OK(mgb_host_restrict(rr, Nf, Nf, Nf, mgWritable(dc), Nc, Nc, Nc));
+        MG_UNLOCK();
+    }
 }
 
 /* reference mg_3d.h:1000-1145 */
@@ -424,7 +492,12 @@ void prolongateAndCorrectError(const double *__restrict__ ec, const int Nc,
                                double *__restrict__ ef, const int Nf)
 {
 #pragma omp single
-    MGB_OK(mgb_host_prolong_correct(ec, Nc, Nc, Nc, ef, Nf, Nf, Nf));
+    {
+        MG_LOCK();
+        const double *er = mgReadable(ec);
+        MGB_OK(mgb_host_prolong_correct(er, Nc, Nc, Nc, mgWritable(ef), Nf, Nf, Nf));
+        MG_UNLOCK();
+    }
 }
 
 /* ---- boundary edge/corner averaging and lexicographic Gauss-Seidel ----
@@ -480,10 +553,13 @@ void GaussSeidelSmoother(double *__restrict__ v, const double *__restrict__ d, c
 static double mgDeviceCycle(void)
 {
     double ss = 0.;
-    mgSyncToDevice();
+    MG_LOCK();
+    mgArrToDevice(mgU);
+    mgArrToDevice(mgD);
     MGB_OK(mgb_vcycle(mgGpu, &ss));
-    mgDeviceChangedSolution();
+    mgArrDeviceWrote(mgU);
     mgPullTimings();
+    MG_UNLOCK();
     return sqrt(ss);
 }
 
@@ -498,15 +574,19 @@ double vcycle(double **uu, double **ff, double **rr, double h, int q, const int 
             mgSingleResult = mgDeviceCycle();
             mgSingleOwner = omp_get_thread_num();
         }
-        return omp_get_thread_num() == mgSingleOwner ? mgSingleResult : 0.;
+        return mgSingleReturn();
     }
     /* any other arrays / entry level: the reference's recursion, operator by
-     * operator on the GPU through the staging entry points */
+     * operator on the GPU */
     double *v = uu[q], *f = ff[q], *res = rr[q];
 #pragma omp single
     {
-        if (q < nLevels - 1)
-            memset(v, 0, sizeof(double) * (size_t)N * N * N);
+        if (q < nLevels - 1) {
+            MG_LOCK();
+            double *w = mgWritable(v);
+            MG_UNLOCK();
+            memset(w, 0, sizeof(double) * (size_t)N * N * N);
+        }
     }
     if (q == 0) {
 #pragma omp single
@@ -529,11 +609,37 @@ double SolverLinSolve()
     return vcycle(u, d, r, spacing, numLevels - 1, numLevels, gsIterNum, finestOneSideNum, A);
 }
 
+/* reference mg_3d.h:1364-1404 (commented out upstream; mg_dirichlet_analytic.c:771-806
+ * is the live copy): the full-multigrid initialisation, on the device, statement for
+ * statement -- see mgb_fmg_init in mgb.h for what that order does.  Call it after the
+ * boundary values are in place, before the V-cycle loop (mg_dirichlet_analytic.c:
+ * 984-989); collective over the OpenMP team like every compute routine. */
+void SolverFMGInitialize()
+{
+#pragma omp single
+    {
+        double ss = 0.;
+        MG_LOCK();
+        mgArrToDevice(mgU);
+        mgArrToDevice(mgD);
+        MGB_OK(mgb_fmg_init(mgGpu, &ss));
+        mgArrDeviceWrote(mgU);
+        MG_UNLOCK();
+    }
+}
+
+/* reference mg_3d.h:1422-1423 -> updateEdgeValues (304-430), on the device copy */
 void SolverSmoothenEdgeValues()
 {
-    mgPull(&mgMirror[0]);
-    updateEdgeValues(u[numLevels - 1], finestOneSideNum);
-    mgTouchedByHost(u[numLevels - 1]);
+#pragma omp single
+    {
+        MG_LOCK();
+        mgArrToDevice(mgU);
+        MGB_OK(mgb_edge_values(mgGpu, numLevels - 1, MGB_U));
+        MGB_OK(mgb_sync(mgGpu));
+        mgArrDeviceWrote(mgU);
+        MG_UNLOCK();
+    }
 }
 
 double SolverGetResidual()
@@ -549,15 +655,20 @@ double SolverGetInitialResidual()
 
 void SolverResetTimingInfo()
 {
+    MG_LOCK();
     MGB_OK(mgb_timing_reset(mgGpu));
+    MG_UNLOCK();
     for (int l = 0; l < numLevels; l++)
         resetTimingInfo(tInfo[l]);
 }
 
 void SolverPrintTimingInfo()
 {
-    if (!mgLazySync)
-        mgPull(&mgMirror[0]); /* explicit mode: the driver reads grid next */
+    if (!mgLazySync) { /* explicit mode: the driver reads grid next */
+        MG_LOCK();
+        mgArrPull(mgU);
+        MG_UNLOCK();
+    }
     for (int l = 0; l < numLevels; l++) {
         printf("LEVEL %d\n", l);
         printTimingInfo(tInfo[l]);
@@ -566,9 +677,13 @@ void SolverPrintTimingInfo()
 
 void SolverFinalize()
 {
-    mgProtect(&mgMirror[0], PROT_READ | PROT_WRITE);
-    mgProtect(&mgMirror[1], PROT_READ | PROT_WRITE);
-    mgMirror[0].host = mgMirror[1].host = NULL;
+    MG_LOCK();
+    for (int t = 0; t < MG_MAX_SESSIONS; t++)
+        mgSessionClose(&mgSessions[t], 1);
+    mgArrRelease(mgU, 0);
+    mgArrRelease(mgD, 0);
+    mgU = mgD = NULL;
+    MG_UNLOCK();
     for (int l = 0; l < numLevels; l++)
         deAllocTimingInfo(&tInfo[l]);
     free(tInfo);
@@ -576,7 +691,9 @@ void SolverFinalize()
     deAllocGridLevels(&u, numLevels);
     deAllocGridLevels(&d, numLevels);
     deAllocGridLevels(&r, numLevels);
+    MG_LOCK();
     MGB_OK(mgb_destroy(mgGpu));
+    MG_UNLOCK();
     mgGpu = NULL;
 }
 

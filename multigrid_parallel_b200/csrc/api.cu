@@ -257,9 +257,7 @@ extern "C" int mgb_destroy(mgb_solver *s)
     if (s->h_scal) cudaFreeHost(s->h_scal);
     if (s->stage) cudaFree(s->stage);
     if (s->lu) cudaFree(s->lu);
-    if (s->band.lb) cudaFree(s->band.lb);
-    if (s->band.ub) cudaFree(s->band.ub);
-    if (s->band.ud) cudaFree(s->band.ud);
+    lu_band_free(&s->band);
     for (PeerSide *ps : {&s->low, &s->up})
         for (void *p : ps->opened)
             cudaIpcCloseMemHandle(p);
@@ -586,13 +584,12 @@ static int create_impl(mgb_solver **out, int ci, int cj, int ck, int levels, int
     if (nc <= MGB_MAX_DENSE_N) {
         s->nc = (int)nc;
         // half bandwidth of the 7-point operator in the ordering p = (i*nj+j)*nk+k
-        s->band.n = s->nc;
-        s->band.bw = cj * ck < s->nc - 1 ? cj * ck : s->nc - 1;
-        const size_t bn = (size_t)s->band.bw * nc;
         CKD(cudaMalloc(&s->lu, sizeof(double) * nc * nc));
-        CKD(cudaMalloc(&s->band.lb, sizeof(double) * (bn ? bn : 1)));
-        CKD(cudaMalloc(&s->band.ub, sizeof(double) * (bn ? bn : 1)));
-        CKD(cudaMalloc(&s->band.ud, sizeof(double) * nc));
+        if (lu_band_alloc(&s->band, s->nc, cj * ck < s->nc - 1 ? cj * ck : s->nc - 1)) {
+            fail("cudaMalloc of the coarse factor's tiles failed");
+            mgb_destroy(s);
+            return 1;
+        }
         LaunchScope ls(s);
         cudaEvent_t e0, e1;
         CKD(cudaEventCreate(&e0));
@@ -872,6 +869,53 @@ extern "C" int mgb_download(mgb_solver *s, int level, int which, double *host)
     return 0;
 }
 
+// a contiguous run of the natural layout: doubles [first, first+count) of the local
+// planes (the unprotectable head / tail fragments of caller-owned arrays, compat/)
+static int range_args(mgb_solver *s, int level, int which, long long first, long long count,
+                      const void *host)
+{
+    if (bind(s) || check_level(s, level, which))
+        return 1;
+    if (!host)
+        return fail("host pointer is null");
+    const Level &lv = s->lv[level];
+    const long long n = (long long)lv.g.li * lv.g.nj * lv.g.nk;
+    if (first < 0 || count < 1 || first + count > n)
+        return fail("range [%lld, %lld) outside the %lld local doubles", first, first + count, n);
+    return 0;
+}
+
+extern "C" int mgb_upload_range(mgb_solver *s, int level, int which, long long first,
+                                long long count, const double *host)
+{
+    if (range_args(s, level, which, first, count, host) || need_stage(s, (size_t)count))
+        return 1;
+    Level &lv = s->lv[level];
+    if (level < s->L - 1)
+        s->coarse_dirty = true;
+    LaunchScope ls(s);
+    CK(cudaMemcpyAsync(s->stage, host, sizeof(double) * count, cudaMemcpyHostToDevice, s->st));
+    launch_pack_range(lv.g, s->stage, lv.a[which].base, first, count, s->st);
+    halo_fence(s, lv);
+    CKLAUNCH();
+    CK(cudaStreamSynchronize(s->st));
+    return halo_status(s);
+}
+
+extern "C" int mgb_download_range(mgb_solver *s, int level, int which, long long first,
+                                  long long count, double *host)
+{
+    if (range_args(s, level, which, first, count, host) || need_stage(s, (size_t)count))
+        return 1;
+    Level &lv = s->lv[level];
+    LaunchScope ls(s);
+    launch_unpack_range(lv.g, lv.a[which].base, s->stage, first, count, s->st);
+    CKLAUNCH();
+    CK(cudaMemcpyAsync(host, s->stage, sizeof(double) * count, cudaMemcpyDeviceToHost, s->st));
+    CK(cudaStreamSynchronize(s->st));
+    return 0;
+}
+
 extern "C" int mgb_zero(mgb_solver *s, int level, int which)
 {
     if (bind(s) || check_level(s, level, which))
@@ -1066,6 +1110,65 @@ static int fetch_scalar(mgb_solver *s, int slot, double *out)
     CK(cudaStreamSynchronize(s->st));
     *out = s->h_scal[slot];
     return halo_status(s);
+}
+
+extern "C" int mgb_edge_values(mgb_solver *s, int level, int which)
+{
+    if (bind(s) || check_level(s, level, which))
+        return 1;
+    Level &lv = s->lv[level];
+    if (lv.dist)
+        return fail("mgb_edge_values: not available on a partitioned level");
+    if (level < s->L - 1)
+        s->coarse_dirty = true;
+    LaunchScope ls(s);
+    launch_edge_values(lv.g, lv.a[which].base, s->st);
+    CKLAUNCH();
+    return 0;
+}
+
+extern "C" int mgb_set_spacing(mgb_solver *s, double h)
+{
+    if (bind(s))
+        return 1;
+    if (s->L != 1)
+        return fail("mgb_set_spacing: only for single-grid sessions (levels == 1): the coarse "
+                    "operator of a hierarchy is built from the spacing at mgb_create");
+    if (!(h > 0.))
+        return fail("spacing must be positive");
+    Level &lv = s->lv[0];
+    lv.h = h;
+    lv.hSq = h * h;            // mg_3d.h:644
+    lv.invHsq = 1. / (h * h);  // mg_3d.h:797
+    drop_graph(s);
+    return 0;
+}
+
+extern "C" int mgb_pin_host(void *p, unsigned long long bytes)
+{
+    if (!p || !bytes)
+        return fail("mgb_pin_host: null range");
+    int ndev = 0;
+    if (mgb_device_count(&ndev) || ndev < 1)
+        return fail("no CUDA device");
+    cudaError_t e = cudaHostRegister(p, (size_t)bytes, cudaHostRegisterPortable);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail("cudaHostRegister(%p, %llu): %s", p, bytes, cudaGetErrorString(e));
+    }
+    return 0;
+}
+
+extern "C" int mgb_unpin_host(void *p)
+{
+    if (!p)
+        return 0;
+    cudaError_t e = cudaHostUnregister(p);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail("cudaHostUnregister(%p): %s", p, cudaGetErrorString(e));
+    }
+    return 0;
 }
 
 extern "C" int mgb_sumsq(mgb_solver *s, int level, int which, double *sumsq)
@@ -1474,7 +1577,11 @@ struct StageTimer {
 // enqueue one cycle from level q down and back up; `count` = bump call counts
 // and (if timed) record stage events.  The residual norm of the finest level
 // lands in d_scal[0].
-static void enqueue_cycle(mgb_solver *s, int q, bool timed)
+// `entry` = the level the cycle was entered at (the finest one for a V-cycle;
+// mgb_fmg_init enters at every level in turn): a coarse entry level holds real
+// data (boundary values on its faces), so it is zeroed for real like
+// mg_3d.h:1258-1259 does, not through the zero-guess short-cut.
+static void enqueue_cycle(mgb_solver *s, int q, bool timed, int entry = -1)
 {
     Level &lv = s->lv[q];
     if (!s->works_on(q))
@@ -1498,7 +1605,7 @@ static void enqueue_cycle(mgb_solver *s, int q, bool timed)
     // 1254-1260: coarse levels start from a zero guess.  With at least one
     // smoothing iteration the level is not zeroed: its first half-sweep treats
     // the guess as 0 and the second one overwrites the other colour
-    const bool zero_guess = q > 0 && q < s->L - 1 && s->opt_zero_guess && s->gs >= 1;
+    const bool zero_guess = q > 0 && q < s->L - 1 && s->opt_zero_guess && s->gs >= 1 && q != entry;
     if (q < s->L - 1 && !zero_guess && q > 0) {
         cudaMemsetAsync(lv.a[MGB_U].base, 0, sizeof(double) * 2 * lv.g.cs, s->st);
         halo_fence(s, lv);
@@ -1536,7 +1643,7 @@ static void enqueue_cycle(mgb_solver *s, int q, bool timed)
     }
     {
         StageTimer t(s, timed, q, MGB_ST_RECURSE);  // 1320
-        enqueue_cycle(s, q - 1, timed);
+        enqueue_cycle(s, q - 1, timed, entry);
         if (s->is_dist() && q == s->LD)
             q_broadcast_agglomerated(s);
     }
@@ -1658,6 +1765,56 @@ extern "C" int mgb_vcycle(mgb_solver *s, double *sumsq)
             return 1;
     }
     bump_calls_like_cycle(s);
+    double v;
+    if (fetch_scalar(s, 0, &v))
+        return 1;
+    if (sumsq)
+        *sumsq = v;
+    return 0;
+}
+
+// SolverFMGInitialize (mg_3d.h:1364-1404, commented out upstream; live against an
+// older vcycle in mg_dirichlet_analytic.c:771-806), statement by statement on the
+// device: boundary values into u[0], the LU solve of d[0] into u[0] (which
+// overwrites them), then per level l = 1 .. L-1: u[l] += P u[l-1] (the full
+// prolongation, all points), boundary values onto the faces of u[l], u[l-1] = 0,
+// one V-cycle entered at level l (which zeroes u[l] again unless l is the finest
+// level, 1254-1260).  Eager launches (a set-up step, not the steady state).
+extern "C" int mgb_fmg_init(mgb_solver *s, double *sumsq)
+{
+    if (bind(s))
+        return 1;
+    if (s->L < 2 || !s->lu)
+        return fail("FMG needs a hierarchy of at least 2 levels");
+    LaunchScope ls(s);
+    std::vector<int> saved = s->calls;
+    {
+        Level &l0 = s->lv[0];
+        if (s->works_on(0)) {
+            launch_set_dirichlet(l0.g, l0.a[MGB_U].base, l0.h, s->st);
+            q_coarse_solve(s);
+        }
+    }
+    for (int l = 1; l < s->L; l++) {
+        Level &f = s->lv[l], &c = s->lv[l - 1];
+        if (s->is_dist() && l == s->LD)
+            q_broadcast_agglomerated(s);  // u[l-1] lives on rank 0
+        q_prolong(s, l, false);
+        if (s->works_on(l)) {
+            launch_set_dirichlet(f.g, f.a[MGB_U].base, f.h, s->st);
+            halo_fence(s, f);
+        }
+        if (s->works_on(l - 1)) {
+            CK(cudaMemsetAsync(c.a[MGB_U].base, 0, sizeof(double) * 2 * c.g.cs, s->st));
+            halo_fence(s, c);
+        }
+        enqueue_cycle(s, l, false, l);
+    }
+    s->calls = saved;
+    s->coarse_dirty = false;  // every coarse u was zeroed on the way up; the cycles keep faces 0
+    CKLAUNCH();
+    if (nccl_status())
+        return 1;
     double v;
     if (fetch_scalar(s, 0, &v))
         return 1;
@@ -1922,23 +2079,21 @@ extern "C" int mgb_host_lu_solve(const double *lu, int n, const double *b, doubl
         return fail("n=%d exceeds MGB_MAX_DENSE_N", n);
     if (n < 1)
         return fail("n < 1");
-    Scratch d, lb, ub, ud, vb, vx;
+    Scratch d, vb, vx;
     CK(cudaMalloc(&d.p, sizeof(double) * (size_t)n * n));
     CK(cudaMalloc(&vb.p, sizeof(double) * n));
     CK(cudaMalloc(&vx.p, sizeof(double) * n));
     CK(cudaMemcpy(d.p, lu, sizeof(double) * (size_t)n * n, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(vb.p, b, sizeof(double) * n, cudaMemcpyHostToDevice));
     // zeros (of either sign) outside the band of the factor contribute nothing
-    LuBand B{};
-    B.n = n;
-    B.bw = lu_bandwidth(d.p, n, 0);
-    const size_t bn = (size_t)B.bw * n;
-    CK(cudaMalloc(&lb.p, sizeof(double) * (bn ? bn : 1)));
-    CK(cudaMalloc(&ub.p, sizeof(double) * (bn ? bn : 1)));
-    CK(cudaMalloc(&ud.p, sizeof(double) * n));
-    B.lb = lb.p; B.ub = ub.p; B.ud = ud.p;
-    launch_lu_extract_band(d.p, B, 0);
-    launch_lu_solve_dense(B, vb.p, vx.p, 0);
+    struct Tiles {
+        LuBand B{};
+        ~Tiles() { lu_band_free(&B); }
+    } tl;
+    if (lu_band_alloc(&tl.B, n, lu_bandwidth(d.p, n, 0)))
+        return fail("cudaMalloc of the factor's tiles failed");
+    launch_lu_extract_band(d.p, tl.B, 0);
+    launch_lu_solve_dense(tl.B, vb.p, vx.p, 0);
     CKLAUNCH();
     CK(cudaMemcpy(x, vx.p, sizeof(double) * n, cudaMemcpyDeviceToHost));
     return 0;

@@ -118,6 +118,50 @@ __global__ void __launch_bounds__(256) k_unpack(Geo g, const double *__restrict_
         dst[ko] = split[(long long)(s ^ 1) * g.cs + t];
 }
 
+// a contiguous run [first, first+n) of the natural layout (local planes) <-> split
+__global__ void __launch_bounds__(256) k_pack_range(Geo g, const double *__restrict__ nat,
+                                                    double *__restrict__ split, long long first,
+                                                    long long n)
+{
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n)
+        return;
+    const long long p = first + t;
+    const int k = (int)(p % g.nk);
+    const long long row = p / g.nk;
+    const int j = (int)(row % g.nj), il = (int)(row / g.nj);
+    const int c = (g.i0 + il + j + k) & 1;
+    split[(long long)c * g.cs + row * g.kh + (k >> 1)] = nat[t];
+}
+
+__global__ void __launch_bounds__(256) k_unpack_range(Geo g, const double *__restrict__ split,
+                                                      double *__restrict__ nat, long long first,
+                                                      long long n)
+{
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n)
+        return;
+    const long long p = first + t;
+    const int k = (int)(p % g.nk);
+    const long long row = p / g.nk;
+    const int j = (int)(row % g.nj), il = (int)(row / g.nj);
+    const int c = (g.i0 + il + j + k) & 1;
+    nat[t] = split[(long long)c * g.cs + row * g.kh + (k >> 1)];
+}
+
+void launch_pack_range(const Geo &g, const double *nat, double *split, long long first,
+                       long long n, cudaStream_t st)
+{
+    k_pack_range<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(g, nat, split, first, n);
+    COUNT_LAUNCH();
+}
+void launch_unpack_range(const Geo &g, const double *split, double *nat, long long first,
+                         long long n, cudaStream_t st)
+{
+    k_unpack_range<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(g, split, nat, first, n);
+    COUNT_LAUNCH();
+}
+
 void launch_finish_sum(const double *partials, int n, double *out, cudaStream_t st)
 {
     k_finish_sum<<<1, 1024, 0, st>>>(partials, n, out);
@@ -1277,6 +1321,66 @@ void launch_halo_wait(const unsigned long long *flag0, unsigned long long *expec
         return;
     k_halo_wait<<<1, 2, 0, st>>>(flag0, expect0, flag1, expect1, timeout_ns, err);
     COUNT_LAUNCH();
+}
+
+// ----------------------------------------------------------------------------
+// updateEdgeValues (mg_3d.h:304-430): every inner point of the 12 edges becomes
+// the mean of its two inward (face) neighbours, then every corner the mean of its
+// three edge neighbours (added in k, j, i order).  Edge updates only read face
+// points, corners read the updated edges: two launches.  Single-GPU levels.
+// ----------------------------------------------------------------------------
+__device__ __forceinline__ long long split_at(const Geo &g, int il, int j, int k)
+{
+    const int c = (g.i0 + il + j + k) & 1;
+    return (long long)c * g.cs + ((long long)il * g.nj + j) * g.kh + (k >> 1);
+}
+
+__global__ void __launch_bounds__(128) k_edge_values(Geo g, double *__restrict__ a)
+{
+    // blockIdx.y: edge 0..11 = axis (0: along i, 1: along j, 2: along k) x the four
+    // (end, end) combinations of the other two axes
+    const int e = blockIdx.y, axis = e >> 2, eb = (e >> 1) & 1, ec = e & 1;
+    const int n[3] = {g.ni, g.nj, g.nk};
+    const int t = 1 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (t > n[axis] - 2)
+        return;
+    const int b = (axis + 1) % 3, c = (axis + 2) % 3;
+    int p[3], q1[3], q2[3];
+    p[axis] = t;
+    p[b] = eb ? n[b] - 1 : 0;
+    p[c] = ec ? n[c] - 1 : 0;
+    for (int x = 0; x < 3; x++)
+        q1[x] = q2[x] = p[x];
+    q1[b] += eb ? -1 : 1;  // inward along b
+    q2[c] += ec ? -1 : 1;  // inward along c
+    // 0.5 * (u[inward neighbour 1] + u[inward neighbour 2]) (mg_3d.h:311-400); a sum of
+    // two terms does not depend on their order, bit for bit
+    const double s = __dadd_rn(a[split_at(g, q1[0], q1[1], q1[2])],
+                               a[split_at(g, q2[0], q2[1], q2[2])]);
+    a[split_at(g, p[0], p[1], p[2])] = __dmul_rn(0.5, s);
+}
+
+__global__ void k_corner_values(Geo g, double *__restrict__ a)
+{
+    const int t = threadIdx.x;  // 8 corners
+    if (t >= 8)
+        return;
+    const int i = (t & 4) ? g.ni - 1 : 0, j = (t & 2) ? g.nj - 1 : 0, k = (t & 1) ? g.nk - 1 : 0;
+    const int ii = i ? i - 1 : 1, jj = j ? j - 1 : 1, kk = k ? k - 1 : 1;
+    // (1./3) * (u[pos+-1] + u[pos+-N] + u[pos+-NN]), left to right (mg_3d.h:405-429)
+    double s = __dadd_rn(a[split_at(g, i, j, kk)], a[split_at(g, i, jj, k)]);
+    s = __dadd_rn(s, a[split_at(g, ii, j, k)]);
+    a[split_at(g, i, j, k)] = __dmul_rn(1. / 3, s);
+}
+
+void launch_edge_values(const Geo &g, double *a, cudaStream_t st)
+{
+    int most = g.ni > g.nj ? g.ni : g.nj;
+    if (g.nk > most)
+        most = g.nk;
+    k_edge_values<<<dim3((most + 127) / 128, 12), 128, 0, st>>>(g, a);
+    k_corner_values<<<1, 32, 0, st>>>(g, a);
+    g_launches += 2;
 }
 
 // ----------------------------------------------------------------------------

@@ -14,6 +14,13 @@ constexpr int kMaxPartials = 1 << 16;
 void launch_pack(const Geo &g, const double *nat, double *split, cudaStream_t st);
 void launch_unpack(const Geo &g, const double *split, double *nat, cudaStream_t st);
 
+// the same for a contiguous run [first, first+n) of the natural layout; `nat` holds
+// just that run
+void launch_pack_range(const Geo &g, const double *nat, double *split, long long first,
+                       long long n, cudaStream_t st);
+void launch_unpack_range(const Geo &g, const double *split, double *nat, long long first,
+                         long long n, cudaStream_t st);
+
 // Dirichlet faces: analytic BCFunc (mg_3d.h:89-90, 1147-1239)
 void launch_set_dirichlet(const Geo &g, double *a, double h, cudaStream_t st);
 
@@ -52,6 +59,9 @@ void launch_prolong_correct(const Geo &gc, const double *ec, const Geo &gf,
 // what the reference's `ef[p] += 0.` does to a boundary value (-0. becomes +0.)
 void launch_add_zero_faces(const Geo &g, double *a, int colour, int il_lo, int il_hi,
                            cudaStream_t st);
+
+// updateEdgeValues (mg_3d.h:304-430) on a whole (unpartitioned) level array
+void launch_edge_values(const Geo &g, double *a, cudaStream_t st);
 
 // sum of squares of the entries of one or two ranges (pads are zero) -> *out
 void launch_sumsq(const double *a0, long long n0, const double *a1, long long n1,
@@ -110,7 +120,9 @@ struct TailP {
     int top;          // levels top .. 0 .. top are done in the kernel
     int gs;           // smoothing iterations per leg
     int zero_top;     // level `top` starts from a zero guess (it is a coarse level)
-    LuBand lu;        // factorised operator of level 0 in band form (n <= 1024)
+    LuBand lu;        // factorised operator of level 0 (tile form)
+    int phase;        // 0: whole sub-cycle in one kernel is not possible any more (the LU
+                      // solve is its own kernel: register budget); 1: down leg, 2: up leg
     TailLevel lv[8];
 };
 void launch_coarse_tail(const TailP &p, cudaStream_t st);
@@ -134,7 +146,10 @@ void launch_coarse_matrix(double *A, int ni, int nj, int nk, double h,
 void launch_lu_factor_band(double *a, int n, int bw, cudaStream_t st);
 // half bandwidth of a dense matrix (max |r-c| over its non-zeros); synchronises
 int lu_bandwidth(const double *a, int n, cudaStream_t st);
-// dense factor -> band arrays (lu_band.cuh); B.lb/ub: bw*n doubles each, B.ud: n
+// storage of the tile form of the factor (lu_band.cuh); returns non-zero on failure
+int lu_band_alloc(LuBand *B, int n, int bw);
+void lu_band_free(LuBand *B);
+// dense factor -> tiles, diagonal and its reciprocal
 void launch_lu_extract_band(const double *a, const LuBand &B, cudaStream_t st);
 // x = (LU)^-1 b in one launch: plain dense vectors, or level 0's colour-split d / u
 void launch_lu_solve_dense(const LuBand &B, const double *b, double *x, cudaStream_t st);

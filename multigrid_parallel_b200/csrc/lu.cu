@@ -137,25 +137,46 @@ int lu_bandwidth(const double *a, int n, cudaStream_t st)
     return bw;
 }
 
-// dense factor -> band arrays of lu_band.cuh
-__global__ void __launch_bounds__(256) k_lu_extract_band(const double *__restrict__ a, LuBand B)
+// dense factor -> 32 x 32 transposed tiles of lu_band.cuh (+ diagonal and its reciprocal)
+__global__ void __launch_bounds__(256) k_lu_extract_tiles(const double *__restrict__ a, LuBand B)
 {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    const int d = blockIdx.y;  // 0: diagonal, 1..bw: distance
-    const int n = B.n;
-    if (i >= n)
-        return;
-    if (d == 0) {
-        B.ud[i] = a[(size_t)i * n + i];
-        return;
+    const int n = B.n, NT = B.nt, NB = (n + 31) >> 5;
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long total = (long long)NB * (NT + 1) * 1024;
+    if (e < n) {
+        const double dg = a[(size_t)e * n + e];
+        B.ud[e] = dg;
+        B.rd[e] = __drcp_rn(dg);
     }
-    B.lb[(size_t)(d - 1) * n + i] = i - d >= 0 ? a[(size_t)i * n + i - d] : 0.;
-    B.ub[(size_t)(d - 1) * n + i] = i + d < n ? a[(size_t)i * n + i + d] : 0.;
+    if (e >= total)
+        return;
+    const int l = (int)(e & 31), jj = (int)((e >> 5) & 31);
+    const int t = (int)((e >> 10) % (NT + 1)), R = (int)((e >> 10) / (NT + 1));
+    const int row = 32 * R + l;
+    // L: column block R-NT+t (t = NT: the diagonal block, strictly lower part)
+    {
+        const int col = 32 * (R - NT + t) + jj;
+        double v = 0.;
+        if (row < n && col >= 0 && col < row)
+            v = a[(size_t)row * n + col];
+        B.lt[e] = v;
+    }
+    // U: column block R+NT-t (t = NT: the diagonal block, strictly upper part)
+    {
+        const int col = 32 * (R + NT - t) + jj;
+        double v = 0.;
+        if (row < n && col < n && col > row)
+            v = a[(size_t)row * n + col];
+        B.ut[e] = v;
+    }
 }
 
 void launch_lu_extract_band(const double *a, const LuBand &B, cudaStream_t st)
 {
-    k_lu_extract_band<<<dim3((B.n + 255) / 256, B.bw + 1), 256, 0, st>>>(a, B);
+    long long total = (long long)lu_tile_doubles(B.n, B.bw);
+    if (total < B.n)
+        total = B.n;
+    k_lu_extract_tiles<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(a, B);
     ++*launch_counter();
 }
 
@@ -171,26 +192,38 @@ k_lu_band_solve(const LuBand B, const Geo g, const double *__restrict__ rhs, dou
     extern __shared__ double lu_sh[];
     const int n = B.n, npad = (n + 31) & ~31;
     double *xs = lu_sh;
-    double *tri = xs + npad;
-    int *flags = reinterpret_cast<int *>(tri + kLuWarps * kLuTriDoubles);
+    int *flags = reinterpret_cast<int *>(xs + npad);  // done_f, done_b, redo
     const int t = threadIdx.x;
-    for (int i = t; i < npad; i += blockDim.x) {
-        double b = 0.;
-        if (i < n) {
-            if (LEVEL) {
-                const int k = i % g.nk, j = (i / g.nk) % g.nj, il = i / (g.nk * g.nj);
-                b = rd_split(g, rhs, il, j, k);
-            } else {
-                b = rhs[i];
+    auto load_b = [&]() {
+        for (int i = t; i < npad; i += blockDim.x) {
+            double b = 0.;
+            if (i < n) {
+                if (LEVEL) {
+                    const int k = i % g.nk, j = (i / g.nk) % g.nj, il = i / (g.nk * g.nj);
+                    b = rd_split(g, rhs, il, j, k);
+                } else {
+                    b = rhs[i];
+                }
             }
+            xs[i] = b;
         }
-        xs[i] = b;
+        if (t < 2)
+            flags[t] = 0;
+    };
+    load_b();
+    if (t == 2)
+        flags[2] = 0;
+    __syncthreads();
+    if (!lu_band_solve<false>(B, xs, flags, t >> 5, t & 31))
+        flags[2] = 1;
+    __syncthreads();
+    if (flags[2]) {  // a fast quotient was not the correctly rounded one: exact divisions
+        __syncthreads();
+        load_b();
+        __syncthreads();
+        lu_band_solve<true>(B, xs, flags, t >> 5, t & 31);
+        __syncthreads();
     }
-    if (t < 2)
-        flags[t] = 0;
-    __syncthreads();
-    lu_band_solve(B, xs, tri, flags, t >> 5, t & 31);
-    __syncthreads();
     for (int i = t; i < n; i += blockDim.x) {
         if (LEVEL) {
             const int k = i % g.nk, j = (i / g.nk) % g.nj, il = i / (g.nk * g.nj);
@@ -206,7 +239,7 @@ template <bool LEVEL>
 static void launch_band_solve(const LuBand &B, const Geo &g, const double *rhs, double *x,
                               cudaStream_t st)
 {
-    const size_t sh = sizeof(double) * lu_solve_smem_doubles(B.n);
+    const size_t sh = sizeof(double) * lu_solve_smem_doubles(B.n) + 16;
     static size_t allowed = 48 * 1024;
     if (sh > allowed) {
         cudaFuncSetAttribute(k_lu_band_solve<LEVEL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -226,6 +259,30 @@ void launch_lu_solve_level(const LuBand &B, const Geo &g, const double *d0, doub
                            cudaStream_t st)
 {
     launch_band_solve<true>(B, g, d0, u0, st);
+}
+
+// storage of the tile form
+int lu_band_alloc(LuBand *B, int n, int bw)
+{
+    B->n = n;
+    B->bw = bw;
+    B->nt = lu_num_tiles(bw);
+    const size_t td = lu_tile_doubles(n, bw);
+    if (cudaMalloc(&B->lt, sizeof(double) * td) != cudaSuccess ||
+        cudaMalloc(&B->ut, sizeof(double) * td) != cudaSuccess ||
+        cudaMalloc(&B->ud, sizeof(double) * n) != cudaSuccess ||
+        cudaMalloc(&B->rd, sizeof(double) * n) != cudaSuccess)
+        return 1;
+    return 0;
+}
+
+void lu_band_free(LuBand *B)
+{
+    if (B->lt) cudaFree(B->lt);
+    if (B->ut) cudaFree(B->ut);
+    if (B->ud) cudaFree(B->ud);
+    if (B->rd) cudaFree(B->rd);
+    B->lt = B->ut = B->ud = B->rd = nullptr;
 }
 
 }  // namespace mgb

@@ -158,36 +158,6 @@ __device__ void t_prolong(const TailLevel &C, const TailLevel &F)
     }
 }
 
-// solveWithLU on level 0 (gauss_elim.h:31-60) through the warp-cooperative
-// band solve of lu_band.cuh; the dense vectors are the natural-layout views of
-// level 0 (mg_3d.h:1270)
-__device__ void t_coarse_solve(const TailLevel &L, const LuBand &B, double *sh)
-{
-    const Geo &g = L.g;
-    const int n = B.n, npad = (n + 31) & ~31;
-    double *xs = sh;
-    double *tri = xs + npad;
-    int *flags = reinterpret_cast<int *>(tri + kLuWarps * kLuTriDoubles);
-    const int t = threadIdx.x;
-    for (int i = t; i < npad; i += kTailThreads) {
-        double b = 0.;
-        if (i < n)
-            b = rd_split(g, L.d, i / (g.nk * g.nj), (i / g.nk) % g.nj, i % g.nk);
-        xs[i] = b;
-    }
-    if (t < 2)
-        flags[t] = 0;
-    __syncthreads();
-    if (t < 32 * kLuWarps)
-        lu_band_solve(B, xs, tri, flags, t >> 5, t & 31);
-    __syncthreads();
-    for (int i = t; i < n; i += kTailThreads) {
-        const int bk = i % g.nk, bj = (i / g.nk) % g.nj, bi = i / (g.nk * g.nj);
-        const int col = (bi + bj + bk) & 1;
-        L.u[(long long)col * g.cs + ((long long)bi * g.nj + bj) * g.kh + (bk >> 1)] = xs[i];
-    }
-}
-
 __device__ void t_zero(const TailLevel &L)
 {
     const long long n = 2 * L.g.cs;
@@ -195,34 +165,36 @@ __device__ void t_zero(const TailLevel &L)
         L.u[t] = 0.;
 }
 
+// phase 1: the down leg (levels top .. 1) and the zero guess of level 0;
+// phase 2: the up leg (levels 1 .. top).  In between the caller launches the
+// coarsest solve (lu.cu): its warps keep three 32-entry tiles in registers,
+// which the 64 registers per thread of a 1024-thread block cannot hold.
 __global__ void __launch_bounds__(kTailThreads) k_coarse_tail(const TailP P)
 {
-    extern __shared__ double tail_sh[];
-    // down (mg_3d.h:1254-1318)
-    for (int q = P.top; q >= 1; q--) {
-        const TailLevel &L = P.lv[q];
-        if (q < P.top || P.zero_top) {  // coarse levels start from a zero guess
-            t_zero(L);
+    if (P.phase == 1) {
+        // down (mg_3d.h:1254-1318)
+        for (int q = P.top; q >= 1; q--) {
+            const TailLevel &L = P.lv[q];
+            if (q < P.top || P.zero_top) {  // coarse levels start from a zero guess
+                t_zero(L);
+                __syncthreads();
+            }
+            for (int it = 0; it < P.gs; it++) {  // preSmoother: RED then BLACK
+                t_half_sweep(L, 1);
+                __syncthreads();
+                t_half_sweep(L, 0);
+                __syncthreads();
+            }
+            t_residual(L);
+            __syncthreads();
+            t_restrict(L, P.lv[q - 1]);
             __syncthreads();
         }
-        for (int it = 0; it < P.gs; it++) {  // preSmoother: RED then BLACK
-            t_half_sweep(L, 1);
-            __syncthreads();
-            t_half_sweep(L, 0);
-            __syncthreads();
-        }
-        t_residual(L);
-        __syncthreads();
-        t_restrict(L, P.lv[q - 1]);
-        __syncthreads();
+        // level 0 (1262-1277): the solve overwrites every entry of u[0]; pads stay 0
+        if (P.top >= 1 || P.zero_top)
+            t_zero(P.lv[0]);
+        return;
     }
-    // level 0 (1262-1277)
-    if (P.top >= 1 || P.zero_top) {
-        t_zero(P.lv[0]);
-        __syncthreads();
-    }
-    t_coarse_solve(P.lv[0], P.lu, tail_sh);
-    __syncthreads();
     // up (1331-1351)
     for (int q = 1; q <= P.top; q++) {
         const TailLevel &L = P.lv[q];
@@ -241,10 +213,16 @@ __global__ void __launch_bounds__(kTailThreads) k_coarse_tail(const TailP P)
 
 void launch_coarse_tail(const TailP &p, cudaStream_t st)
 {
-    // n <= 1024: at most 8 KB of xs + the triangle tiles, under the 48 KB default
-    const size_t sh = sizeof(double) * lu_solve_smem_doubles(p.lu.n);
-    k_coarse_tail<<<1, kTailThreads, sh, st>>>(p);
+    TailP q = p;
+    q.phase = 1;
+    k_coarse_tail<<<1, kTailThreads, 0, st>>>(q);
     ++*launch_counter();
+    launch_lu_solve_level(p.lu, p.lv[0].g, p.lv[0].d, p.lv[0].u, st);
+    if (p.top >= 1) {
+        q.phase = 2;
+        k_coarse_tail<<<1, kTailThreads, 0, st>>>(q);
+        ++*launch_counter();
+    }
 }
 
 }  // namespace mgb

@@ -133,6 +133,13 @@ class Solver:
     def set_dirichlet(self, level, which):
         check(self.L.mgb_set_dirichlet(self.h_, level, which))
 
+    def edge_values(self, level, which):
+        """updateEdgeValues (mg_3d.h:304-430) on the device array"""
+        check(self.L.mgb_edge_values(self.h_, level, which))
+
+    def set_spacing(self, h):
+        check(self.L.mgb_set_spacing(self.h_, h))
+
     def sumsq(self, level, which):
         v = C.c_double()
         check(self.L.mgb_sumsq(self.h_, level, which, v))
@@ -193,6 +200,12 @@ class Solver:
         """one V-cycle; returns the residual 2-norm (SolverLinSolve)"""
         v = C.c_double()
         check(self.L.mgb_vcycle(self.h_, v))
+        return math.sqrt(v.value)
+
+    def fmg_init(self):
+        """SolverFMGInitialize (mg_3d.h:1364-1404); returns the residual 2-norm after it"""
+        v = C.c_double()
+        check(self.L.mgb_fmg_init(self.h_, v))
         return math.sqrt(v.value)
 
     def solve(self, threshold, max_cycles=100):

@@ -74,12 +74,28 @@ def main():
                  "tol": 1e-8, "init_norm": init, "cycles": len(hist),
                  "history": [float(x) for x in hist], "seconds": secs}
         entry.update(checksums(u, 1.0 / (N - 1)))
-        out[key] = entry
+        out.setdefault(key, {}).update(entry)  # keeps history_exact (gen_exact_history.py)
         print(key, "N", N, "cycles", len(hist), "last", hist[-1], "err", entry["errnorm_np"],
               f"{secs:.2f}s", flush=True)
         del u
         json.dump(out, open(path, "w"), indent=1)
     ref.set_threads(1)
+
+    # FMG initialisation (SolverFMGInitialize, mg_3d.h:1364-1404, restated on the live
+    # functions by oracle/ref_harness.c:ref_fmg_init): every level right after it, and
+    # the solve that follows
+    fmg = {}
+    for coarse, levels, gs in [(3, 5, 2), (3, 7, 2), (5, 4, 1)]:
+        ref.set_threads(1)
+        state = ref.fmg_state(coarse, levels, gs)
+        hist, init, u, _ = ref.solve(coarse, levels, gs, tol=1e-8, max_cycles=60, fmg=True)
+        fmg[f"{coarse}_{levels}_{gs}"] = {
+            "coarse": coarse, "levels": levels, "gs": gs,
+            "u_sha256": [sha(uu) for uu, dd in state], "d_sha256": [sha(dd) for uu, dd in state],
+            "init_norm": init, "cycles_after_fmg": len(hist), "history": [float(x) for x in hist],
+            "solution_sha256": sha(u)}
+        print("fmg", coarse, levels, gs, "cycles after", len(hist), flush=True)
+    json.dump(fmg, open(os.path.join(GOLD, "fmg.json"), "w"), indent=1)
 
     # operator-level fixtures on seeded inputs
     ops = {}

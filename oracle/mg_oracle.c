@@ -344,6 +344,39 @@ double orc_mg_vcycle(orc_mg *m)
     return cycle_level(m, m->levels - 1, m->h);
 }
 
+void orc_mg_fmg_init(orc_mg *m)
+{
+    /* mg_3d.h:1364-1404 (commented there; live against an older vcycle in
+     * mg_dirichlet_analytic.c:771-806), statement by statement, for boxes:
+     * BCs into u[0] -- overwritten by the LU solve of d[0] -- then per level:
+     * interpolate the coarser solution into u[l], BCs onto its faces, zero
+     * u[l-1], one V-cycle entered at level l (which zeroes u[l] again unless l
+     * is the finest level, 1254-1260). */
+    double h = m->h * (1 << (m->levels - 1)); /* = GRID_LENGTH/(coarseGridNum-1) */
+    orc_set_dirichlet(m->u[0], m->ni[0], m->nj[0], m->nk[0], h);
+    orc_lu_solve(m->lu, m->ni[0] * m->nj[0] * m->nk[0], m->d[0], m->u[0]);
+    for (int l = 1; l < m->levels; l++) {
+        h = h * 0.5;
+        orc_prolong_correct(m->u[l - 1], m->ni[l - 1], m->nj[l - 1], m->nk[l - 1], m->u[l],
+                            m->ni[l], m->nj[l], m->nk[l]);
+        orc_set_dirichlet(m->u[l], m->ni[l], m->nj[l], m->nk[l], h);
+        memset(m->u[l - 1], 0,
+               sizeof(double) * (size_t)m->ni[l - 1] * m->nj[l - 1] * m->nk[l - 1]);
+        cycle_level(m, l, h);
+    }
+}
+
+/* test_mg_3d.c:17-29 on the finest level; returns ||d|| */
+double orc_mg_setup_problem(orc_mg *m)
+{
+    const int L = m->levels - 1;
+    const int ni = m->ni[L], nj = m->nj[L], nk = m->nk[L];
+    orc_set_dirichlet(m->d[L], ni, nj, nk, m->h);
+    const double init = orc_l2norm(m->d[L], (long)ni * nj * nk);
+    orc_set_dirichlet(m->u[L], ni, nj, nk, m->h);
+    return init;
+}
+
 int orc_mg_solve(orc_mg *m, double tol, int max_cycles, double *history,
                  double *init_norm)
 {

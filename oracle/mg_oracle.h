@@ -75,6 +75,12 @@ double orc_mg_h(const orc_mg *m);
 /* one V-cycle from the finest level; returns the post-smoothing residual norm */
 double orc_mg_vcycle(orc_mg *m);
 
+/* SolverFMGInitialize (mg_3d.h:1364-1404, commented out upstream) restated on
+ * the functions above; see mg_oracle.c for what the statement order implies */
+void orc_mg_fmg_init(orc_mg *m);
+/* test_mg_3d.c:17-29: BCs into the faces of d and u on the finest level; returns ||d|| */
+double orc_mg_setup_problem(orc_mg *m);
+
 /* test_mg_3d.c:8-68 flow: BCs into d and u, threshold tol*||d||, cycle until
  * norm <= threshold or max_cycles; history[c] = norm after cycle c+1.
  * Returns the number of cycles run. */

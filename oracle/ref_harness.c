@@ -158,16 +158,77 @@ double ref_timed_cycles(int n, double *last_norm)
     return t1 - t0;
 }
 
+/* Full-multigrid initialisation.  The reference carries SolverFMGInitialize only
+ * as a commented-out block (mg_3d.h:1364-1404; a live copy against an older
+ * vcycle signature sits in mg_dirichlet_analytic.c:771-806, behind `useFMG`,
+ * 984-989).  These are those statements, in that order, on today's functions:
+ * the only edit is vcycle's current argument list (res array and spacing,
+ * mg_3d.h:1242).  Note what that order does, and what the goldens therefore pin:
+ * the LU solve overwrites the boundary values just put into u[0], and vcycle
+ * itself zeroes its entry level whenever that is not the finest one (1254-1260). */
+void ref_fmg_init(void)
+{
+    int N = coarseGridNum;
+    const int totalNodes = N * N * N;
+    double h = GRID_LENGTH / (coarseGridNum - 1);
+    setupBoundaryConditions(u[0], N, h);
+    solveWithLU(A, totalNodes, d[0], u[0]);
+    for (int l = 1; l < numLevels; l++) {
+        const int Nc = N;
+        N = 2 * N - 1;
+        h = h * 0.5;
+#pragma omp parallel
+        {
+            prolongateAndCorrectError(u[l - 1], Nc, u[l], N);
+        }
+        setupBoundaryConditions(u[l], N, h);
+        memset(u[l - 1], 0, sizeof(double) * Nc * Nc * Nc);
+#pragma omp parallel
+        {
+            vcycle(u, d, r, h, l, numLevels, gsIterNum, N, A);
+        }
+    }
+}
+
+/* the set-up of test_mg_3d.c:17-29 on an open solver; returns ||d|| */
+double ref_setup_problem(void)
+{
+    SolverSetupBoundaryConditions();
+    double init = SolverGetInitialResidual();
+    setupBoundaryConditions(u[numLevels - 1], finestOneSideNum, spacing);
+    return init;
+}
+
 /* test_mg_3d.c:17-67; history[c] = norm after cycle c+1; returns cycles */
+static int solve_flow(int coarse, int levels, int gs, double tol, int max_cycles, int use_fmg,
+                      double *history, double *init_norm, double *u_out, double *seconds);
+
 int ref_solve(int coarse, int levels, int gs, double tol, int max_cycles,
               double *history, double *init_norm, double *u_out,
               double *seconds)
+{
+    return solve_flow(coarse, levels, gs, tol, max_cycles, 0, history, init_norm, u_out, seconds);
+}
+
+/* the same flow with the FMG initialisation where mg_dirichlet_analytic.c:984-989
+ * puts it: after the set-up, before the V-cycle loop */
+int ref_solve_fmg(int coarse, int levels, int gs, double tol, int max_cycles,
+                  double *history, double *init_norm, double *u_out,
+                  double *seconds)
+{
+    return solve_flow(coarse, levels, gs, tol, max_cycles, 1, history, init_norm, u_out, seconds);
+}
+
+static int solve_flow(int coarse, int levels, int gs, double tol, int max_cycles, int use_fmg,
+                      double *history, double *init_norm, double *u_out, double *seconds)
 {
     double *grid, *rhs, h;
     int N = ref_solver_open(coarse, levels, gs, &grid, &rhs, &h);
     SolverSetupBoundaryConditions();
     double init = SolverGetInitialResidual();
     setupBoundaryConditions(grid, N, h);
+    if (use_fmg)
+        ref_fmg_init();
     if (init_norm)
         *init_norm = init;
     double cmp = init * tol, norm = 1e9;

@@ -71,6 +71,9 @@ class Orc:
         L.orc_mg_vcycle.argtypes = [C.c_void_p]
         L.orc_mg_solve.restype = i
         L.orc_mg_solve.argtypes = [C.c_void_p, d, i, p, p]
+        L.orc_mg_fmg_init.argtypes = [C.c_void_p]
+        L.orc_mg_setup_problem.restype = d
+        L.orc_mg_setup_problem.argtypes = [C.c_void_p]
 
     # array-level helpers (arrays are float64, shape (ni,nj,nk), C order)
     def set_dirichlet(self, v, h):
@@ -153,6 +156,13 @@ class OrcMG:
     def vcycle(self):
         return self.L.orc_mg_vcycle(self.h_)
 
+    def setup_problem(self):
+        """test_mg_3d.c:17-29; returns ||d||"""
+        return self.L.orc_mg_setup_problem(self.h_)
+
+    def fmg_init(self):
+        self.L.orc_mg_fmg_init(self.h_)
+
     def solve(self, tol=1e-8, max_cycles=100):
         hist = np.zeros(max_cycles)
         init = np.zeros(1)
@@ -186,6 +196,9 @@ class Ref:
         L.ref_l2norm.argtypes = [p, i]
         L.ref_solve.restype = i
         L.ref_solve.argtypes = [i, i, i, d, i, p, p, p, p]
+        L.ref_solve_fmg.restype = i
+        L.ref_solve_fmg.argtypes = [i, i, i, d, i, p, p, p, p]
+        L.ref_setup_problem.restype = d
         L.ref_solver_open.restype = i
         L.ref_solver_open.argtypes = [i, i, i, C.POINTER(p), C.POINTER(p), p]
         L.ref_vcycle.restype = d
@@ -229,15 +242,29 @@ class Ref:
         self.L.ref_lu_solve(_p(lu), lu.shape[0], _p(b), _p(x))
         return x
 
-    def solve(self, coarse, levels, gs, tol=1e-8, max_cycles=100, want_u=True):
+    def solve(self, coarse, levels, gs, tol=1e-8, max_cycles=100, want_u=True, fmg=False):
         N = (coarse - 1) * (1 << (levels - 1)) + 1
         hist = np.zeros(max_cycles)
         init = np.zeros(1)
         secs = np.zeros(1)
         u = np.zeros((N, N, N)) if want_u else None
-        n = self.L.ref_solve(coarse, levels, gs, tol, max_cycles, _p(hist),
-                             _p(init), _p(u), _p(secs))
+        fn = self.L.ref_solve_fmg if fmg else self.L.ref_solve
+        n = fn(coarse, levels, gs, tol, max_cycles, _p(hist), _p(init), _p(u), _p(secs))
         return hist[:n].copy(), float(init[0]), u, float(secs[0])
+
+    def fmg_state(self, coarse, levels, gs):
+        """every level's u and d right after the set-up + FMG initialisation"""
+        grid, rhs, h = c_dp(), c_dp(), C.c_double()
+        self.L.ref_solver_open(coarse, levels, gs, C.byref(grid), C.byref(rhs), C.byref(h))
+        self.L.ref_setup_problem()
+        self.L.ref_fmg_init()
+        out = []
+        for l in range(levels):
+            n = (coarse - 1) * (1 << l) + 1
+            out.append((np.ctypeslib.as_array(self.L.ref_level_u(l), shape=(n, n, n)).copy(),
+                        np.ctypeslib.as_array(self.L.ref_level_d(l), shape=(n, n, n)).copy()))
+        self.L.ref_solver_close()
+        return out
 
 
 def seeded(shape, seed):

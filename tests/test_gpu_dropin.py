@@ -75,26 +75,59 @@ def test_reference_driver_usage_error(tmp_path):
     assert p.returncode == 1 and p.stdout.startswith("Usage:")  # mg_3d.h:109-113
 
 
-@pytest.mark.parametrize("threads,lazy,profile", [(1, "1", "1"), (3, "1", "0"), (2, "0", "1")])
-def test_example_driver(tmp_path, orc, threads, lazy, profile):
+def _session_expected(orc, rnd):
+    """the device-resident session flow of poisson_dirichlet.c, on the oracle"""
+    P = 65
+    hp = 1.0 / (P - 1) * (0.5 if rnd else 1.0)
+    v = np.zeros((P,) * 3)
+    orc.set_dirichlet(v, hp)
+    f = np.zeros(P ** 3)
+    t = np.arange(0, P ** 3, 7)
+    f[t] = 1e-3 * (t % 13).astype(np.float64) * (rnd + 1)
+    f = f.reshape((P,) * 3)
+    last = 0.0
+    for it in range(6):
+        orc.smooth(v, f, hp, 1, True)
+        orc.smooth(v, f, hp, 1, False)
+        last = orc.residual(v, f, hp)
+        if it == 2:
+            v[P // 2, P // 2, P // 2] += 0.25
+        if it == 3:
+            v[0, 1, 1] -= 0.125
+    return v, last
+
+
+@pytest.mark.parametrize("threads,lazy,profile,fmg", [(1, "1", "1", False), (3, "1", "0", False),
+                                                      (2, "0", "1", False), (4, "1", "1", True),
+                                                      (1, "0", "0", True)])
+def test_example_driver(tmp_path, orc, threads, lazy, profile, fmg):
     exe = os.path.join(BUILD, "poisson_dirichlet")
     assert os.path.exists(exe), "run __graft_entry__.build() first"
-    out = _run(exe, [3, 5, 2], tmp_path, threads,
-               {"MGB_LAZY_SYNC": lazy, "MGB_PROFILE": profile})
+    env = {"MGB_LAZY_SYNC": lazy, "MGB_PROFILE": profile, "MGB_DUMP_DIR": str(tmp_path)}
+    if fmg:
+        env["MGB_USE_FMG"] = "1"
+    out = _run(exe, [3, 5, 2], tmp_path, threads, env)
     gold = json.load(open(os.path.join(GOLD, "histories.json")))["3_5_2"]
     kv = {}
     for line in out.splitlines():
         parts = line.split()
         if parts:
             kv.setdefault(parts[0], []).append(parts[1:])
-    assert int(kv["cycles"][0][0]) == gold["cycles"]
     norms = [float(p[2]) for p in kv["cycle"]]
-    assert np.allclose(norms, gold["history"], rtol=1e-12, atol=0)
+    if fmg:  # SolverFMGInitialize, then the loop: the reference's own numbers for that flow
+        gf = json.load(open(os.path.join(GOLD, "fmg.json")))["3_5_2"]
+        assert int(kv["cycles"][0][0]) == gf["cycles_after_fmg"]
+        assert np.allclose(norms, gf["history"], rtol=1e-12, atol=0)
+        assert float(kv["fmg_residual"][0][0]) == pytest.approx(gold["history"][0], rel=1e-12)
+    else:
+        assert int(kv["cycles"][0][0]) == gold["cycles"]
+        assert np.allclose(norms, gold["history"], rtol=1e-12, atol=0)
     assert float(kv["N"][0][4]) == gold["init_norm"]  # serial host sum: identical
     err = kv["errnorm"][0]
-    assert float(err[4]) == gold["probe_1_2_3"]
-    assert float(err[0]) == pytest.approx(gold["errnorm_np"], rel=1e-9)
-    assert float(err[2]) == pytest.approx(gold["sumsq_np"], rel=1e-13)
+    if not fmg:
+        assert float(err[4]) == gold["probe_1_2_3"]
+        assert float(err[0]) == pytest.approx(gold["errnorm_np"], rel=1e-9)
+        assert float(err[2]) == pytest.approx(gold["sumsq_np"], rel=1e-13)
     # host write between solves reached the GPU: residual jumped, second solve
     # needed cycles and restored the analytic value
     assert float(kv["perturbed_residual"][0][0]) > 1e3
@@ -102,6 +135,8 @@ def test_example_driver(tmp_path, orc, threads, lazy, profile):
     assert int(c2[0]) >= 5 and int(c2[2]) == int(c2[0])
     if lazy == "1":  # explicit mode only syncs at its documented API points
         assert float(kv["restored"][0][0]) < 1e-7
+        # SolverSmoothenEdgeValues on the device == updateEdgeValues on the host copy
+        assert kv["edges_equal"][0][0] == "1"
     # raw-pointer smoother on caller arrays == oracle
     M = 17
     hm = 1.0 / (M - 1)
@@ -114,6 +149,15 @@ def test_example_driver(tmp_path, orc, threads, lazy, profile):
     rb = kv["rbgs17"][0]
     assert float(rb[1]) == pytest.approx(init, rel=1e-13)
     assert float(rb[3]) == pytest.approx(after, rel=1e-13)
+    # device-resident sessions for large caller-owned arrays (lazy mode; staged per call
+    # in explicit mode): host writes in between are seen, the final array read straight
+    # from the caller's memory equals the oracle's bit for bit
+    for rnd in (0, 1):
+        want, last = _session_expected(orc, rnd)
+        got = np.fromfile(tmp_path / f"session{rnd}.bin", dtype=np.float64).reshape(want.shape)
+        assert np.array_equal(got.view(np.uint64), want.view(np.uint64)), f"session {rnd}"
+        line = kv[f"session{rnd}"][0]
+        assert float(line[1]) == pytest.approx(last, rel=1e-13)
 
 
 def test_example_driver_vtk(tmp_path):

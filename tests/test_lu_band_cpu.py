@@ -1,4 +1,4 @@
-"""CPU model of the band-limited LU of csrc/lu.cu + csrc/lu_band.cuh.
+"""CPU model of the band-limited, tiled LU of csrc/lu.cu + csrc/lu_band.cuh.
 
 The GPU kernels restrict the reference's dense loops (gauss_elim.h:9-60) to the
 band of the coarse operator and re-schedule the solve over warps.  This file
@@ -8,7 +8,9 @@ must be finished before this chunk" arithmetic -- and checks it against the
 oracle's dense loops BIT FOR BIT (sign of zero included for the factor).  The
 -m gpu tests then check the kernels themselves against the same oracle.
 """
+import math
 import struct
+from fractions import Fraction
 
 import numpy as np
 import pytest
@@ -40,94 +42,116 @@ def band_factor_model(a, bw):
     return a
 
 
-def extract_band(lu, bw):
+def fma(a, b, c):
+    """correctly rounded a*b + c (Python 3.12 has no math.fma), signed zeros included"""
+    r = Fraction(a) * Fraction(b) + Fraction(c)
+    if r != 0:
+        return float(r)
+    if a == 0 or b == 0:  # (+-0) + c with c = +-0: -0 only if both are -0
+        prod_neg = math.copysign(1.0, a) * math.copysign(1.0, b) < 0
+        if c == 0:
+            return -0.0 if prod_neg and math.copysign(1.0, c) < 0 else 0.0
+    return 0.0  # exact cancellation of non-zeros: +0 in round-to-nearest
+
+
+def extract_tiles(lu, bw):
+    """k_lu_extract_tiles: per block row NT+1 transposed 32x32 tiles of L and of U"""
     n = lu.shape[0]
-    lb = np.zeros((max(bw, 1), n))
-    ub = np.zeros((max(bw, 1), n))
-    for d in range(1, bw + 1):
-        for i in range(n):
-            if i - d >= 0:
-                lb[d - 1, i] = lu[i, i - d]
-            if i + d < n:
-                ub[d - 1, i] = lu[i, i + d]
-    return lb, ub, np.diag(lu).copy()
+    NT, NB = (bw + 31) // 32, (n + 31) // 32
+    lt = np.zeros((NB, NT + 1, 32, 32))
+    ut = np.zeros((NB, NT + 1, 32, 32))
+    for R in range(NB):
+        for t in range(NT + 1):
+            for jj in range(32):
+                for l in range(32):
+                    row = 32 * R + l
+                    col = 32 * (R - NT + t) + jj
+                    if row < n and 0 <= col < row:
+                        lt[R, t, jj, l] = lu[row, col]
+                    col = 32 * (R + NT - t) + jj
+                    if row < n and row < col < n:
+                        ut[R, t, jj, l] = lu[row, col]
+    ud = np.diag(lu).copy()
+    return lt, ut, ud, 1.0 / ud, NT
 
 
-def band_solve_model(lb, ub, ud, bw, b):
-    """lu_band_solve, blocks processed in publication order; asserts that every
-    value a chunk reads belongs to a block the chunk waited for"""
+def tile_solve_model(lt, ut, ud, rd, NT, b, exact):
+    """lu_band_solve<EXACT>, blocks processed in publication order; asserts that every
+    block a tile reads has been published; returns (x, every fast quotient was the
+    correctly rounded one)"""
     n = len(b)
     NB = (n + 31) // 32
     xs = [float(v) for v in b] + [0.0] * (NB * 32 - n)
+    ok = True
     done_f = 0
     for R in range(NB):
-        i0 = 32 * R
         sums = [0.0] * 32
-        dmax = min(bw, i0 + 31)
-        dc = dmax
-        while dc >= 1:
-            dlow = max(dc - 15, 1)
-            jmax = min(i0 + 31 - dlow, i0 - 1)
-            need = (jmax >> 5) + 1 if jmax >= 0 else 0
-            assert done_f >= need
-            for t in range(16):
-                d = dc - t
-                for lane in range(32):
-                    i = i0 + lane
-                    if i < n and d >= 1 and d > lane and d <= i:
-                        assert (i - d) >> 5 < need  # a finished block
-                        sums[lane] = sums[lane] + lb[d - 1, i] * xs[i - d]
-            dc -= 16
+        order = [(t, R - NT + t) for t in range(NT - 1)]
+        if NT >= 1 and R >= 1:
+            order.append((NT - 1, R - 1))
+        for t, P in order:
+            if P < 0:
+                continue
+            assert done_f >= P + 1
+            for jj in range(32):
+                for l in range(32):
+                    sums[l] = sums[l] + lt[R, t, jj, l] * xs[32 * P + jj]
         assert done_f >= R
-        tri = [[(lb[lane - jj - 1, i0 + lane] if (i0 + lane < n and lane - jj <= bw) else 0.0)
-                for jj in range(lane)] for lane in range(32)]
-        bi = [xs[i0 + lane] if i0 + lane < n else 0.0 for lane in range(32)]
+        bi = [xs[32 * R + l] if 32 * R + l < n else 0.0 for l in range(32)]
         mine = [0.0] * 32
         for jj in range(32):
             z = bi[jj] - sums[jj]
             mine[jj] = z
-            for lane in range(jj + 1, 32):
-                sums[lane] = sums[lane] + tri[lane][jj] * z
-        for lane in range(32):
-            if i0 + lane < n:
-                xs[i0 + lane] = mine[lane]
+            for l in range(32):
+                sums[l] = sums[l] + lt[R, NT, jj, l] * z
+        for l in range(32):
+            if 32 * R + l < n:
+                xs[32 * R + l] = mine[l]
         done_f = R + 1
     done_b = 0
     for Rr in range(NB):
         R = NB - 1 - Rr
-        i0 = 32 * R
         sums = [0.0] * 32
-        dmax = min(bw, n - 1 - i0)
-        dc = dmax
-        while dc >= 1:
-            dlow = max(dc - 15, 1)
-            jmin = i0 + max(dlow, 32)
-            need = NB - (jmin >> 5) if jmin < n else 0
-            assert done_b >= need
-            for t in range(16):
-                d = dc - t
-                for lane in range(32):
-                    i = i0 + lane
-                    if i < n and d >= 1 and d > 31 - lane and i + d < n:
-                        assert NB - 1 - ((i + d) >> 5) < need
-                        sums[lane] = sums[lane] + ub[d - 1, i] * xs[i + d]
-            dc -= 16
+        order = [(t, R + NT - t) for t in range(NT - 1)]
+        if NT >= 1 and R + 1 < NB:
+            order.append((NT - 1, R + 1))
+        for t, P in order:
+            if P >= NB:
+                continue
+            assert done_b >= NB - P
+            for jj in range(31, -1, -1):
+                for l in range(32):
+                    sums[l] = sums[l] + ut[R, t, jj, l] * xs[32 * P + jj]
         assert done_b >= Rr
-        zi = [xs[i0 + lane] if i0 + lane < n else 0.0 for lane in range(32)]
-        di = [ud[i0 + lane] if i0 + lane < n else 1.0 for lane in range(32)]
+        zi = [xs[32 * R + l] if 32 * R + l < n else 0.0 for l in range(32)]
+        di = [ud[32 * R + l] if 32 * R + l < n else 1.0 for l in range(32)]
+        yi = [rd[32 * R + l] if 32 * R + l < n else 1.0 for l in range(32)]
         mine = [0.0] * 32
         for jj in range(31, -1, -1):
-            x = (zi[jj] - sums[jj]) / di[jj]
+            t_ = zi[jj] - sums[jj]
+            if exact:
+                x = t_ / di[jj]
+            else:
+                q0 = t_ * yi[jj]
+                x = fma(fma(-di[jj], q0, t_), yi[jj], q0)
+                if struct.pack("<d", x) != struct.pack("<d", t_ / di[jj]):
+                    ok = False
             mine[jj] = x
-            for lane in range(jj):
-                u = ub[jj - lane - 1, i0 + lane] if (i0 + lane < n and jj - lane <= bw and
-                                                    i0 + jj < n) else 0.0
-                sums[lane] = sums[lane] + u * x
-        for lane in range(32):
-            if i0 + lane < n:
-                xs[i0 + lane] = mine[lane]
+            for l in range(32):
+                sums[l] = sums[l] + ut[R, NT, jj, l] * x
+        for l in range(32):
+            if 32 * R + l < n:
+                xs[32 * R + l] = mine[l]
         done_b = Rr + 1
-    return np.array(xs[:n])
+    return np.array(xs[:n]), ok
+
+
+def band_solve_model(lu, bw, b):
+    lt, ut, ud, rd, NT = extract_tiles(lu, bw)
+    x, ok = tile_solve_model(lt, ut, ud, rd, NT, b, exact=False)
+    if not ok:  # the kernel's fallback
+        x, _ = tile_solve_model(lt, ut, ud, rd, NT, b, exact=True)
+    return x, ok
 
 
 @pytest.mark.parametrize("coarse", [(3, 3, 3), (5, 3, 3), (3, 5, 3), (5, 5, 3), (9, 3, 3)])
@@ -140,12 +164,12 @@ def test_band_model_equals_dense_oracle(orc, coarse):
     orc.lu_factor(want)
     got = band_factor_model(A, bw)
     assert np.array_equal(bits(got), bits(want)), "factor (sign of zero included)"
-    lb, ub, ud = extract_band(got, bw)
     for seed in (1, 2):
         b = seeded((n,), seed)
         x_want = orc.lu_solve(want, b)
-        x_got = band_solve_model(lb, ub, ud, bw, b)
+        x_got, fast_ok = band_solve_model(got, bw, b)
         assert np.array_equal(bits(x_got), bits(x_want))
+        assert fast_ok, "the fast quotient should practically always be the rounded one"
 
 
 def test_band_model_on_a_generic_banded_matrix(orc):
@@ -163,9 +187,26 @@ def test_band_model_on_a_generic_banded_matrix(orc):
     orc.lu_factor(want)
     got = band_factor_model(A, bw)
     assert np.array_equal(bits(got), bits(want))
-    lb, ub, ud = extract_band(got, bw)
     b = seeded((n,), 6)
-    assert np.array_equal(bits(band_solve_model(lb, ub, ud, bw, b)), bits(orc.lu_solve(want, b)))
+    assert np.array_equal(bits(band_solve_model(got, bw, b)[0]), bits(orc.lu_solve(want, b)))
+
+
+def test_fast_quotient_is_the_rounded_quotient():
+    """q = fma(fma(-d, t*y, t), y, t*y) with y = RN(1/d) against t/d on random pairs, plus
+    signed zeros and large magnitudes (the kernel checks every quotient it forms)"""
+    rng = np.random.Generator(np.random.PCG64(7))
+    n = 20000
+    t = rng.uniform(-1, 1, n) * 10.0 ** rng.integers(-30, 30, n)
+    d = rng.uniform(0.5, 4, n) * rng.choice([-1.0, 1.0], n) * 2.0 ** rng.integers(-20, 20, n)
+    t[:6] = [0.0, -0.0, 1.0, -1.0, 3.0, 1e300]
+    d[:6] = [-6.0, -6.0, 3.0, 3.0, 1.0, 2.0]
+    bad = 0
+    for a, b in zip(t.tolist(), d.tolist()):
+        y = 1.0 / b
+        q0 = a * y
+        q = fma(fma(-b, q0, a), y, q0)
+        bad += struct.pack("<d", q) != struct.pack("<d", a / b)
+    assert bad == 0
 
 
 def test_signed_zero_multipliers_outside_the_band(orc):
