@@ -347,6 +347,10 @@ def run_ours(args):
     strong = None if args.no_extras else _leg(B.strong1025, world, rank, local_rank)
     c5 = None if args.no_extras else _leg(B.config5, world)
 
+    dropin = None
+    if world == 1 and not args.no_extras:
+        dropin = _leg(B.dropin_e2e, local_rank)
+
     cpu = None
     if rank == 0 and not args.no_cpu_baseline:
         try:
@@ -387,6 +391,8 @@ def run_ours(args):
             line["strong1025"] = strong
         if c5 is not None:
             line["config5"] = c5
+        if dropin is not None:
+            line["e2e_dropin"] = dropin
         print(json.dumps(line), flush=True)
     D.barrier()
     return 0

@@ -267,3 +267,46 @@ def config5(world, steps=10, warmup=3):
     out["n_gpus"] = world
     out["lu_solve_share_of_cycle"] = out["lu_solve_us"] * 1e-3 / out["ms_per_cycle"]
     return out
+
+
+def dropin_e2e(device):
+    """BASELINE config 3 as the reference's user runs it: the UNMODIFIED test_mg_3d.c
+    compiled against the drop-in headers (compat/_build/test_mg_3d_gpu, built where the
+    reference's sources are mounted), `3 9 2`, default settings; the ASCII VTK (8 GB) goes
+    to /dev/null.  Returns the driver's own `Overall time for solving` (its timed region,
+    test_mg_3d.c:36-68) and the wall time of the whole program."""
+    import re
+    import subprocess
+    import tempfile
+    exe = os.path.join(ROOT, "multigrid_parallel_b200", "compat", "_build", "test_mg_3d_gpu")
+    if not os.path.exists(exe):
+        return {"unavailable": "compat/_build/test_mg_3d_gpu not prebuilt (needs the reference's "
+                               "test_mg_3d.c at build time)"}
+    try:
+        threads = len(os.sched_getaffinity(0))
+    except AttributeError:
+        threads = os.cpu_count() or 1
+    with tempfile.TemporaryDirectory() as tmp:
+        os.symlink("/dev/null", os.path.join(tmp, "diff2.vtk"))
+        env = dict(os.environ, OMP_NUM_THREADS=str(threads), MGB_VTK_TIMING="1",
+                   MGB_DEVICE=str(device))
+        t0 = time.perf_counter()
+        p = subprocess.run([exe, "3", "9", "2"], cwd=tmp, env=env, capture_output=True, text=True,
+                           timeout=900)
+        wall = time.perf_counter() - t0
+    if p.returncode != 0:
+        return {"error": (p.stdout[-300:] + p.stderr[-300:])}
+    secs = float(re.search(r"^Overall time for solving:\s*(\S+)", p.stdout, re.M).group(1))
+    cycles = len(re.findall(r"Residual Norm:", p.stdout))
+    err = re.search(r"^Error norm:\s*(\S+)", p.stdout, re.M).group(1)
+    vtk = re.search(r"writeOutputData .*: 513\^3 points, (\d+) threads, ([0-9.]+) s", p.stderr)
+    dof = 513.0 ** 3
+    return {"program": "the reference's unmodified test_mg_3d.c on compat/mg_3d.h, args 3 9 2, "
+                       f"{threads} OpenMP threads, MGB_PROFILE=1 (per-stage timing, eager launches), "
+                       "lazy page-protection coherence",
+            "overall_time_for_solving_s": secs, "cycles": cycles,
+            "value": dof * cycles / secs, "unit": "DOF*cycles/s",
+            "error_norm_printed": err, "whole_program_wall_s": wall,
+            "vtk_formatting_s": float(vtk.group(2)) if vtk else None,
+            "vtk_note": "ASCII legacy VTK of 513^3 points (8 GB) formatted in parallel on the host, "
+                        "byte-identical to the reference's writer, written to /dev/null"}

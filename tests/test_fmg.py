@@ -95,7 +95,11 @@ def test_gpu_fmg_matches_reference_golden(mgb, key, tail):
             assert sha(s.download(l, mgb.MGB_D)) == g["d_sha256"][l], f"d level {l}"
         hist = s.solve(g["init_norm"] * 1e-8, 60)
         assert len(hist) == g["cycles_after_fmg"]
-        assert np.allclose(hist, g["history"], rtol=1e-12, atol=0)
+        # the reference's printed norms are sequential sums over N^3 squares: they differ
+        # from the exactly rounded sum by 5e-14 at 33^3 and 5e-12 at 129^3 (DESIGN.md
+        # section 3); the solution below is compared bit for bit
+        rtol = 1e-12 if g["levels"] <= 5 else 2e-11
+        assert np.allclose(hist, g["history"], rtol=rtol, atol=0)
         assert sha(s.download(top, mgb.MGB_U)) == g["solution_sha256"]
         assert first > hist[0]
 

@@ -67,6 +67,37 @@ def test_reference_driver_unmodified(tmp_path, threads, lazy):
     assert got_sha == want_sha
 
 
+def test_reference_driver_unmodified_513(tmp_path):
+    """BASELINE config 3 literally: the reference's own driver, `test_mg_3d 3 9 2`, on the
+    drop-in headers (default settings: lazy coherence, per-stage timing).  The 8 GB ASCII
+    VTK goes to /dev/null; its formatting time is reported."""
+    exe = os.path.join(BUILD, "test_mg_3d_gpu")
+    if not os.path.exists(exe):
+        pytest.skip("test_mg_3d_gpu not prebuilt (needs /root/reference at build time)")
+    os.symlink("/dev/null", tmp_path / "diff2.vtk")
+    threads = len(os.sched_getaffinity(0))
+    env = dict(os.environ, OMP_NUM_THREADS=str(threads), MGB_VTK_TIMING="1")
+    p = subprocess.run([exe, "3", "9", "2"], cwd=tmp_path, env=env, capture_output=True, text=True,
+                       timeout=1200)
+    assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-2000:]
+    gold = json.load(open(os.path.join(GOLD, "histories.json")))["3_9_2"]
+    got = _residual_lines(p.stdout)
+    assert len(got) == gold["cycles"] == 16
+    # printed with %20g (6 digits); the reference's own sequential sums differ from the
+    # exactly rounded ones by 2.6e-10 at this size (DESIGN.md section 3)
+    for (ci, gn, _), want in zip(got, gold["history"]):
+        assert float(gn) == pytest.approx(want, rel=6e-6)
+    err = float(re.search(r"^Error norm:\s*(\S+)", p.stdout, re.M).group(1))
+    assert err == pytest.approx(gold["errnorm_np"], rel=1e-5)  # %10.6g
+    secs = float(re.search(r"^Overall time for solving:\s*(\S+)", p.stdout, re.M).group(1))
+    assert 0 < secs < 60
+    assert p.stdout.count("LEVEL ") == 9
+    vtk = re.search(r"writeOutputData .*: 513\^3 points, (\d+) threads, ([0-9.]+) s", p.stderr)
+    assert vtk, p.stderr[-500:]
+    print(f"test_mg_3d 3 9 2 on the drop-in: Overall time for solving {secs:.4f} s, "
+          f"VTK formatting {vtk.group(2)} s on {vtk.group(1)} threads")
+
+
 def test_reference_driver_usage_error(tmp_path):
     exe = os.path.join(BUILD, "test_mg_3d_gpu")
     if not os.path.exists(exe):
