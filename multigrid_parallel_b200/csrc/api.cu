@@ -171,21 +171,30 @@ struct mgb_solver {
     // by events, so that a halo exchange can overlap the interior of a sweep
     cudaStream_t st_comm = nullptr;
     cudaEvent_t ev_m2c = nullptr, ev_c2m = nullptr;
-    int opt_overlap = 0;
-    // halo planes over NVLink peer memory instead of ncclSend/Recv:
-    // xflags[0]/[1] = sequence flags written by the lower / upper neighbour,
-    // [2]/[3] = my sequence numbers towards up / low, [4]/[5] = what I expect
-    // next from low / up, [6]/[7] = block counters of the push kernels
+    // halo planes over NVLink peer memory instead of ncclSend/Recv, fused into the
+    // compute kernels (halo.cuh).  xflags = this rank's flag block (XF_* slots), mapped
+    // by the peers; n_* = sends issued so far in the open epoch (counted identically on
+    // every rank, whether or not it has a neighbour on that side)
     int opt_p2p = 1;
     PeerSide low, up;
     unsigned long long *xflags = nullptr;
+    unsigned long long n_up = 0, n_low = 0, n_gather = 0, n_norm = 0;
+    // levels < LD: computed redundantly on EVERY rank from an all-gathered right-hand
+    // side (P2P path) instead of on rank 0 with a gather + broadcast (NCCL path)
+    bool replicate = false;
+    struct PeerAny {
+        unsigned long long *xf = nullptr;  // its flag block
+        double *d_coarse = nullptr;        // its d array of level LD-1 (colour 0, plane 0)
+    };
+    std::vector<PeerAny> peers;  // [rank]
+    std::vector<void *> peers_opened;
     // a halo wait that gives up (MGB_HALO_TIMEOUT_S, default 300 s, 0 = never) sets
     // bits here (host-mapped) instead of trapping; checked after every synchronisation
     unsigned int *h_halo_err = nullptr, *d_halo_err = nullptr;
     unsigned long long halo_timeout_ns = 300ULL * 1000000000ULL;
     bool is_dist() const { return nranks > 1; }
     // does this rank compute on level q?
-    bool works_on(int q) const { return nranks == 1 || q >= LD || rank == 0; }
+    bool works_on(int q) const { return nranks == 1 || q >= LD || rank == 0 || replicate; }
 };
 
 struct LaunchScope {
@@ -239,7 +248,8 @@ extern "C" int mgb_destroy(mgb_solver *s)
     if (s->comm && s->xflags) {
         // collective: the neighbours have my arrays mapped (CUDA IPC) and may still be
         // pushing into them; nobody frees anything before everybody has got here
-        nccl().AllReduce(s->xflags + 8, s->xflags + 8, 1, ncclInt, ncclSum, s->comm, s->st);
+        nccl().AllReduce(s->xflags + XF_SCRATCH, s->xflags + XF_SCRATCH, 1, ncclInt, ncclSum,
+                         s->comm, s->st);
         cudaStreamSynchronize(s->st);
     }
     if (s->h_halo_err) cudaFreeHost(s->h_halo_err);
@@ -261,6 +271,8 @@ extern "C" int mgb_destroy(mgb_solver *s)
     for (PeerSide *ps : {&s->low, &s->up})
         for (void *p : ps->opened)
             cudaIpcCloseMemHandle(p);
+    for (void *p : s->peers_opened)
+        cudaIpcCloseMemHandle(p);
     if (s->xflags) cudaFree(s->xflags);
     if (s->comm) nccl().CommDestroy(s->comm);
     if (s->st_comm) { cudaStreamSynchronize(s->st_comm); cudaStreamDestroy(s->st_comm); }
@@ -348,10 +360,27 @@ static Geo rank_geo(const Geo &mine, int nranks, int r)
     return make_geo(mine.ni, mine.nj, mine.nk, hi - lo + lower + upper, lo - lower);
 }
 
-// returns 0 when both neighbours are mapped; any failure leaves the solver on
-// the NCCL path (the caller makes the decision collective)
+// returns 0 when everything is mapped; any failure leaves the solver on the NCCL
+// path (the caller makes the decision collective).  records per rank: [0] its flag
+// block, [1 + 2*(l-LD) + w] array w (U, D) of partitioned level l, [count-1] the rhs
+// array of the first replicated level LD-1
 static int setup_p2p_local(mgb_solver *s, std::vector<IpcRec> &all, int count)
 {
+    // one cudaMalloc block is opened once, however many pointers into it are needed
+    std::vector<std::pair<IpcRec, void *>> seen;
+    auto map = [&](const IpcRec &rec) -> void * {
+        for (auto &e : seen)
+            if (!memcmp(&e.first.h, &rec.h, sizeof rec.h))
+                return (char *)e.second + rec.offset;
+        void *base = nullptr;
+        if (cudaIpcOpenMemHandle(&base, rec.h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+            cudaGetLastError();
+            return nullptr;
+        }
+        s->peers_opened.push_back(base);
+        seen.push_back({rec, base});
+        return (char *)base + rec.offset;
+    };
     for (int side = 0; side < 2; side++) {
         const int r = side == 0 ? s->rank - 1 : s->rank + 1;
         PeerSide &ps = side == 0 ? s->low : s->up;
@@ -360,20 +389,6 @@ static int setup_p2p_local(mgb_solver *s, std::vector<IpcRec> &all, int count)
         ps.arr[0].assign(s->L, nullptr);
         ps.arr[1].assign(s->L, nullptr);
         ps.g.assign(s->L, Geo{});
-        std::vector<std::pair<IpcRec, void *>> seen;
-        auto map = [&](const IpcRec &rec) -> void * {
-            for (auto &e : seen)
-                if (!memcmp(&e.first.h, &rec.h, sizeof rec.h))
-                    return (char *)e.second + rec.offset;
-            void *base = nullptr;
-            if (cudaIpcOpenMemHandle(&base, rec.h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
-                cudaGetLastError();
-                return nullptr;
-            }
-            ps.opened.push_back(base);
-            seen.push_back({rec, base});
-            return (char *)base + rec.offset;
-        };
         const IpcRec *recs = &all[(size_t)r * count];
         ps.flags = (unsigned long long *)map(recs[0]);
         if (!ps.flags)
@@ -387,6 +402,19 @@ static int setup_p2p_local(mgb_solver *s, std::vector<IpcRec> &all, int count)
                 ps.g[l] = rank_geo(s->lv[l].g, s->nranks, r);
             }
         ps.present = true;
+    }
+    // the all-gather in front of the replicated coarse levels and the exchange of norm
+    // partials talk to ALL peers, not just to the neighbours
+    s->peers.assign(s->nranks, mgb_solver::PeerAny{});
+    for (int r = 0; r < s->nranks; r++) {
+        if (r == s->rank)
+            continue;
+        const IpcRec *recs = &all[(size_t)r * count];
+        void *xf = map(recs[0]), *dc = map(recs[count - 1]);
+        if (!xf || !dc)
+            return 1;
+        s->peers[r].xf = (unsigned long long *)xf;
+        s->peers[r].d_coarse = (double *)dc + MGB_GUARD;
     }
     return 0;
 }
@@ -404,15 +432,21 @@ static int setup_p2p(mgb_solver *s)
         else
             ok = 0;
     }
-    const int count = 1 + 2 * (s->L - s->LD);
+    const int count = 2 + 2 * (s->L - s->LD);
     std::vector<IpcRec> mine(count), all((size_t)count * s->nranks);
     if (cudaMalloc(&s->xflags, 4096) != cudaSuccess || cudaMemset(s->xflags, 0, 4096) != cudaSuccess)
         ok = 0;
+    if (ok) {  // epochs start at 1 (0 = "nothing sent yet" for every flag)
+        const unsigned long long one = 1;
+        ok = cudaMemcpy(s->xflags + XF_EPOCH, &one, sizeof one, cudaMemcpyHostToDevice) == cudaSuccess;
+    }
     if (ok) {
         ok = ipc_record(range, s->xflags, &mine[0]);
         for (int l = s->LD; ok && l < s->L; l++)
             for (int w = 0; ok && w < 2; w++)
                 ok = ipc_record(range, s->lv[l].a[w].alloc, &mine[1 + 2 * (l - s->LD) + w]);
+        if (ok)
+            ok = ipc_record(range, s->lv[s->LD - 1].a[MGB_D].alloc, &mine[count - 1]);
     }
     // everybody learns everybody's handles (the exchange itself is collective
     // even if this rank already failed)
@@ -439,6 +473,7 @@ static int setup_p2p(mgb_solver *s)
     cudaFree(dsend);
     cudaFree(drecv);
     s->opt_p2p = ok;
+    s->replicate = ok != 0;
     if (getenv("MGB_VERBOSE"))
         fprintf(stderr, "mgb: rank %d halo exchange over %s\n", s->rank,
                 ok ? "NVLink peer memory (P2P stores + flags)" : "ncclSend/ncclRecv");
@@ -619,8 +654,6 @@ static int create_impl(mgb_solver **out, int ci, int cj, int ck, int levels, int
         CKD(cudaStreamCreateWithFlags(&s->st_comm, cudaStreamNonBlocking));
         CKD(cudaEventCreateWithFlags(&s->ev_m2c, cudaEventDisableTiming));
         CKD(cudaEventCreateWithFlags(&s->ev_c2m, cudaEventDisableTiming));
-        if (getenv("MGB_OVERLAP"))
-            s->opt_overlap = atoi(getenv("MGB_OVERLAP")) != 0;
         ncclUniqueId id;
         memcpy(&id, uid, sizeof id);
         ncclResult_t r = nccl().CommInitRank(&s->comm, nranks, id, rank);
@@ -684,9 +717,18 @@ extern "C" int mgb_create_dist(mgb_solver **out, int ci, int cj, int ck, int lev
         return fail("nccl_uid128 is null");
     if (nranks & (nranks - 1))
         return fail("nranks must be a power of two (got %d)", nranks);
+    // defaults: a level is partitioned while every rank owns >= 2 planes (an even number)
+    // and the level as a whole has >= 2^20 points; the levels below are replicated:
+    // computed redundantly on every rank from an all-gathered right-hand side.  Measured on
+    // 2 B200s: a half-sweep on a slab of a small level costs kernel + ~7 us of flag latency
+    // (every step has to hear from the neighbour), the same kernel on the whole level ~4 us
+    // while that level is latency-bound (up to ~65^3..129^3 points).  The threshold is on
+    // the GLOBAL size because a replicated level costs every rank the whole level, which
+    // grows with the number of GPUs in weak scaling.
     return create_impl(out, ci, cj, ck, levels, gs_iters, device, rank, nranks, nccl_uid128,
-                       min_planes_per_rank > 0 ? min_planes_per_rank : 16,
-                       min_points_per_rank >= 0 ? min_points_per_rank : (1LL << 20));
+                       min_planes_per_rank > 0 ? min_planes_per_rank : 2,
+                       min_points_per_rank >= 0 ? min_points_per_rank
+                                                : (1LL << 20) / (nranks > 0 ? nranks : 1));
 }
 
 extern "C" int mgb_dist_info(const mgb_solver *s, int *rank, int *nranks, int *first_dist_level)
@@ -814,6 +856,7 @@ extern "C" int mgb_sync(mgb_solver *s)
 // level arrays across the boundary
 // ----------------------------------------------------------------------------
 static void halo_fence(mgb_solver *s, Level &lv);  // P2P halo exchange, below
+static void close_epoch(mgb_solver *s);
 
 static int need_stage(mgb_solver *s, size_t n)
 {
@@ -846,6 +889,7 @@ extern "C" int mgb_upload(mgb_solver *s, int level, int which, const double *hos
     CK(cudaMemcpyAsync(s->stage, host, sizeof(double) * n, cudaMemcpyHostToDevice, s->st));
     launch_pack(lv.g, s->stage, lv.a[which].base, s->st);
     halo_fence(s, lv);
+    close_epoch(s);
     CKLAUNCH();
     CK(cudaStreamSynchronize(s->st));
     return halo_status(s);
@@ -897,6 +941,7 @@ extern "C" int mgb_upload_range(mgb_solver *s, int level, int which, long long f
     CK(cudaMemcpyAsync(s->stage, host, sizeof(double) * count, cudaMemcpyHostToDevice, s->st));
     launch_pack_range(lv.g, s->stage, lv.a[which].base, first, count, s->st);
     halo_fence(s, lv);
+    close_epoch(s);
     CKLAUNCH();
     CK(cudaStreamSynchronize(s->st));
     return halo_status(s);
@@ -923,6 +968,7 @@ extern "C" int mgb_zero(mgb_solver *s, int level, int which)
     Level &lv = s->lv[level];
     CK(cudaMemsetAsync(lv.a[which].base, 0, sizeof(double) * 2 * lv.g.cs, s->st));
     halo_fence(s, lv);
+    close_epoch(s);
     return 0;
 }
 
@@ -936,6 +982,7 @@ extern "C" int mgb_set_dirichlet(mgb_solver *s, int level, int which)
     LaunchScope ls(s);
     launch_set_dirichlet(lv.g, lv.a[which].base, lv.h, s->st);
     halo_fence(s, lv);
+    close_epoch(s);
     CKLAUNCH();
     return 0;
 }
@@ -983,11 +1030,118 @@ static void comm_end(mgb_solver *s)
     cudaStreamWaitEvent(s->st, s->ev_c2m, 0);
 }
 
-// sum a device scalar over the ranks (rank order is NCCL's, fixed per topology)
+// ---- the fused halo protocol (halo.cuh): host side ----------------------------
+// What a kernel on a partitioned level gets: "wait for everything both neighbours were
+// asked to send so far" (no pushes yet -- the caller adds those AFTER taking this, so
+// that a kernel never waits for its own sends' counterparts)
+static HaloCtl make_ctl(mgb_solver *s, const Level &lv)
+{
+    HaloCtl h{};
+    h.push_up.plane[0] = h.push_up.plane[1] = -1;
+    h.push_low.plane[0] = h.push_low.plane[1] = -1;
+    if (!lv.dist || !s->opt_p2p)
+        return h;  // epoch == nullptr: no halo work
+    h.epoch = s->xflags + XF_EPOCH;
+    // the lower neighbour's up-sends are counted by my own n_up (same program on every rank)
+    if (s->rank > 0)
+        h.wait_low = HaloWait{s->xflags + XF_FROM_LOW, s->xflags + XF_PREV_UP, s->n_up};
+    if (s->rank < s->nranks - 1)
+        h.wait_up = HaloWait{s->xflags + XF_FROM_UP, s->xflags + XF_PREV_LOW, s->n_low};
+    h.timeout_ns = s->halo_timeout_ns;
+    h.err = s->d_halo_err;
+    return h;
+}
+
+// a half-sweep of `colour` on partitioned level q also feeds the neighbours' halos: its
+// planes own_hi-2 and own_hi-1 are the upper neighbour's two lower halo planes, own_lo is
+// the lower neighbour's upper halo plane
+static void add_sweep_push(mgb_solver *s, int q, int colour, HaloCtl &h)
+{
+    Level &lv = s->lv[q];
+    const Geo &g = lv.g;
+    ++s->n_up;
+    ++s->n_low;
+    if (s->rank < s->nranks - 1) {
+        const Geo &gn = s->up.g[q];
+        HaloPush &p = h.push_up;
+        for (int k = 0; k < 2; k++) {
+            const int gp = lv.own_hi - 1 - k;  // global plane
+            p.plane[k] = gp - g.i0;
+            p.dst[k] = s->up.arr[MGB_U][q] + (long long)colour * gn.cs + (long long)(gp - gn.i0) * gn.pj;
+        }
+        p.peer_flag = s->up.flags + XF_FROM_LOW;
+        p.count = (unsigned int *)(s->xflags + XF_CNT_UP);
+        p.off = s->n_up;
+    }
+    if (s->rank > 0) {
+        const Geo &gn = s->low.g[q];
+        HaloPush &p = h.push_low;
+        p.plane[0] = lv.own_lo - g.i0;
+        p.plane[1] = -1;
+        p.dst[0] = s->low.arr[MGB_U][q] + (long long)colour * gn.cs + (long long)(lv.own_lo - gn.i0) * gn.pj;
+        p.dst[1] = nullptr;
+        p.peer_flag = s->low.flags + XF_FROM_UP;
+        p.count = (unsigned int *)(s->xflags + XF_CNT_LOW);
+        p.off = s->n_low;
+    }
+}
+
+// the fused residual+restriction of level q into partitioned level q-1: my last coarse
+// plane is the upper neighbour's coarse-rhs halo (it feeds the NEXT restriction)
+static void add_coarse_rhs_push(mgb_solver *s, int qc, HaloCtl &h)
+{
+    Level &c = s->lv[qc];
+    ++s->n_up;
+    if (s->rank < s->nranks - 1) {
+        const Geo &gn = s->up.g[qc];
+        HaloPush &p = h.push_up;
+        const int gp = c.own_hi - 1;
+        p.plane[0] = gp - c.g.i0;
+        p.plane[1] = -1;
+        for (int col = 0; col < 2; col++)
+            p.dst[col] = s->up.arr[MGB_D][qc] + (long long)col * gn.cs + (long long)(gp - gn.i0) * gn.pj;
+        p.peer_flag = s->up.flags + XF_FROM_LOW;
+        p.count = (unsigned int *)(s->xflags + XF_CNT_UP);
+        p.off = s->n_up;
+    }
+}
+
+// end of a collective operation on the P2P path: remember the last sends, open the next
+// epoch (one tiny kernel; inside a captured cycle it is the graph's last node)
+static void close_epoch(mgb_solver *s)
+{
+    if (!s->is_dist() || !s->opt_p2p)
+        return;
+    launch_epoch_close(s->xflags, s->n_up, s->n_low, s->st);
+    s->n_up = s->n_low = s->n_gather = s->n_norm = 0;
+}
+struct Collective {
+    mgb_solver *s;
+    explicit Collective(mgb_solver *s_) : s(s_) {}
+    ~Collective() { close_epoch(s); }
+};
+
+// sum a device scalar over the ranks: P2P path in RANK ORDER on every rank (bitwise the
+// same everywhere and from run to run), NCCL path in NCCL's order
 static void allreduce_scalar(mgb_solver *s, int slot)
 {
     if (!s->is_dist())
         return;
+    if (s->opt_p2p) {
+        NormHost g{};
+        g.me = s->rank;
+        g.nranks = s->nranks;
+        g.scalar = s->d_scal + slot;
+        for (int r = 0; r < s->nranks; r++)
+            g.peer_xf[r] = s->peers[r].xf;
+        g.my_xf = s->xflags;
+        g.off = ++s->n_norm;
+        g.timeout_ns = s->halo_timeout_ns;
+        g.err = s->d_halo_err;
+        launch_norm_exchange(g, s->st);
+        s->nccl_calls++;
+        return;
+    }
     comm_begin(s);
     NC(nccl().AllReduce(s->d_scal + slot, s->d_scal + slot, 1, ncclDouble, ncclSum, s->comm,
                         nccl_stream(s)));
@@ -995,112 +1149,107 @@ static void allreduce_scalar(mgb_solver *s, int slot)
     s->nccl_calls++;
 }
 
-// one halo step on array `a` of a partitioned level, colours in `mask`
-// (bit c = colour c).  Planes are global indices, -1 = nothing:
-//   send_up   -> upper neighbour stores it as the same global plane
-//   recv_low  <- lower neighbour's send_up
-//   send_down -> lower neighbour;  recv_up <- upper neighbour's send_down
-// phases of a halo step: the P2P path can separate the push of my planes from
-// the wait for the neighbours' (other work goes in between); NCCL does both in
-// HALO_PUSH and nothing in HALO_WAIT
-enum { HALO_BOTH = 0, HALO_PUSH = 1, HALO_WAIT = 2 };
-
-// `bracket` (NCCL path): order the exchange after the kernel stream and make the
-// kernel stream wait for it (false: the caller places comm_begin / comm_end itself)
-static void halo_step(mgb_solver *s, Level &lv, double *a, int mask, int send_up, int recv_low,
-                      int send_down, int recv_up, bool bracket = true, int phase = HALO_BOTH)
+// one EXPLICIT halo step on array `a` of a partitioned level, colours in `mask`
+// (bit c = colour c): uploads, fences, stand-alone calls -- the cycle's own exchanges
+// ride inside its kernels.  Planes are global indices, -1 = nothing:
+//   send_up / send_up2 -> upper neighbour stores them as the same global planes
+//   send_down          -> lower neighbour
+// `dir`: bit 0 = something goes up, bit 1 = something goes down (the same on every rank,
+// whether or not it has that neighbour: sends are counted identically everywhere).
+// NCCL path: one grouped send/recv per step, ordered in the receiver's stream.
+static void halo_step(mgb_solver *s, Level &lv, double *a, int mask, int send_up, int send_up2,
+                      int send_down, int dir)
 {
     const Geo &g = lv.g;
     const bool has_low = s->rank > 0, has_up = s->rank < s->nranks - 1;
+    const int q = (int)(&lv - &s->lv[0]);
+    const int w = a == lv.a[MGB_U].base ? MGB_U : MGB_D;
     if (s->opt_p2p) {
-        const int q = (int)(&lv - &s->lv[0]);
-        const int w = a == lv.a[MGB_U].base ? MGB_U : MGB_D;
-        if (phase != HALO_WAIT) {
-            HaloRun run[2];  // 0: to the upper neighbour, 1: to the lower
-            for (int dir = 0; dir < 2; dir++) {
-                const PeerSide &ps = dir == 0 ? s->up : s->low;
-                const int plane = dir == 0 ? send_up : send_down;
-                if (!(dir == 0 ? has_up : has_low) || plane < 0)
+        HaloRun run[2];  // 0: to the upper neighbour, 1: to the lower
+        if (dir & 1)
+            ++s->n_up;
+        if (dir & 2)
+            ++s->n_low;
+        for (int d = 0; d < 2; d++) {
+            if (!(dir & (1 << d)) || !(d == 0 ? has_up : has_low))
+                continue;
+            const PeerSide &ps = d == 0 ? s->up : s->low;
+            const Geo &gn = ps.g[q];
+            const int planes[2] = {d == 0 ? send_up : send_down, d == 0 ? send_up2 : -1};
+            int k = 0;
+            for (int pi = 0; pi < 2; pi++) {
+                if (planes[pi] < 0)
                     continue;
-                const Geo &gn = ps.g[q];
-                int k = 0;
                 for (int c = 0; c < 2; c++) {
                     if (!(mask & (1 << c)))
                         continue;
-                    run[dir].src[k] = a + (long long)c * g.cs + (long long)(plane - g.i0) * g.pj;
-                    run[dir].dst[k] =
-                        ps.arr[w][q] + (long long)c * gn.cs + (long long)(plane - gn.i0) * gn.pj;
-                    run[dir].n[k] = g.pj;
+                    run[d].src[k] = a + (long long)c * g.cs + (long long)(planes[pi] - g.i0) * g.pj;
+                    run[d].dst[k] = ps.arr[w][q] + (long long)c * gn.cs +
+                                    (long long)(planes[pi] - gn.i0) * gn.pj;
+                    run[d].n[k] = g.pj;
                     k++;
                 }
-                // the neighbour's flag I write: its "from low" if I am below it
-                run[dir].peer_flag = ps.flags + (dir == 0 ? 0 : 1);
-                run[dir].seq = s->xflags + (dir == 0 ? 2 : 3);
-                run[dir].done = (unsigned int *)(s->xflags + (dir == 0 ? 6 : 7));
             }
-            launch_halo_push(run[0], run[1], s->st);
+            run[d].peer_flag = ps.flags + (d == 0 ? XF_FROM_LOW : XF_FROM_UP);
+            run[d].count = (unsigned int *)(s->xflags + (d == 0 ? XF_CNT_UP : XF_CNT_LOW));
+            run[d].off = d == 0 ? s->n_up : s->n_low;
         }
-        if (phase != HALO_PUSH) {
-            const bool wl = has_low && recv_low >= 0, wu = has_up && recv_up >= 0;
-            launch_halo_wait(wl ? s->xflags + 0 : nullptr, s->xflags + 4,
-                             wu ? s->xflags + 1 : nullptr, s->xflags + 5, s->halo_timeout_ns,
-                             s->d_halo_err, s->st);
-        }
+        launch_halo_push(run[0], run[1], s->xflags + XF_EPOCH, s->st);
+        launch_halo_wait(make_ctl(s, lv), s->st);
         s->nccl_calls++;
         return;
     }
-    if (phase == HALO_WAIT)
-        return;
-    if (bracket)
-        comm_begin(s);
+    comm_begin(s);
     NC(nccl().GroupStart());
     for (int c = 0; c < 2; c++) {
         if (!(mask & (1 << c)))
             continue;
         double *base = a + (long long)c * g.cs;
         const size_t n = (size_t)g.pj;
-        if (has_up && send_up >= 0)
-            NC(nccl().Send(base + (long long)(send_up - g.i0) * g.pj, n, ncclDouble, s->rank + 1,
-                           s->comm, s->st_comm));
-        if (has_low && recv_low >= 0)
-            NC(nccl().Recv(base + (long long)(recv_low - g.i0) * g.pj, n, ncclDouble,
-                           s->rank - 1, s->comm, s->st_comm));
-        if (has_low && send_down >= 0)
-            NC(nccl().Send(base + (long long)(send_down - g.i0) * g.pj, n, ncclDouble,
-                           s->rank - 1, s->comm, s->st_comm));
-        if (has_up && recv_up >= 0)
-            NC(nccl().Recv(base + (long long)(recv_up - g.i0) * g.pj, n, ncclDouble, s->rank + 1,
-                           s->comm, s->st_comm));
+        const int ups[2] = {send_up, send_up2};
+        for (int pi = 0; pi < 2; pi++) {
+            if (!(dir & 1) || ups[pi] < 0)
+                continue;
+            if (has_up)
+                NC(nccl().Send(base + (long long)(ups[pi] - g.i0) * g.pj, n, ncclDouble, s->rank + 1,
+                               s->comm, s->st_comm));
+            if (has_low)  // the lower neighbour's same step: its plane at the same distance
+                NC(nccl().Recv(base + (long long)(lv.own_lo - (lv.own_hi - ups[pi]) - g.i0) * g.pj, n,
+                               ncclDouble, s->rank - 1, s->comm, s->st_comm));
+        }
+        if ((dir & 2) && send_down >= 0) {
+            if (has_low)
+                NC(nccl().Send(base + (long long)(send_down - g.i0) * g.pj, n, ncclDouble,
+                               s->rank - 1, s->comm, s->st_comm));
+            if (has_up)
+                NC(nccl().Recv(base + (long long)(lv.own_hi + (send_down - lv.own_lo) - g.i0) * g.pj, n,
+                               ncclDouble, s->rank + 1, s->comm, s->st_comm));
+        }
     }
     NC(nccl().GroupEnd());
-    if (bracket)
-        comm_end(s);
+    comm_end(s);
     s->nccl_calls++;
 }
 
-// P2P path only.  A push lands in the neighbour's halo planes whenever the
-// SENDER gets there; ncclRecv, by contrast, is ordered in the receiver's stream.
-// Wherever a rank writes its own halo planes with a local kernel (the zero
-// guess of a coarse level, the redundant halo update of the prolongation,
-// uploads), it therefore tells both neighbours when that is done, and waits
-// for the same from them, before anybody pushes into those planes again: a
-// data-less halo step.
+// P2P path only.  A push lands in the neighbour's halo planes whenever the SENDER gets
+// there; ncclRecv, by contrast, is ordered in the receiver's stream.  Wherever a rank
+// writes its own halo planes with a local kernel (uploads, mgb_zero, the full-colour
+// prolongation), it therefore tells both neighbours when that is done, and waits for the
+// same from them, before anybody pushes into those planes again: a data-less halo step.
 static void halo_fence(mgb_solver *s, Level &lv)
 {
     if (!lv.dist || !s->opt_p2p)
         return;
-    halo_step(s, lv, lv.a[MGB_U].base, 0, 0, 0, 0, 0);
+    halo_step(s, lv, lv.a[MGB_U].base, 0, -1, -1, -1, 3);
 }
 
-// after a half-sweep of `colour`: the freshly written boundary planes go to
-// the neighbours' halos (one colour-plane per neighbour)
-static void halo_after_sweep(mgb_solver *s, Level &lv, int colour, bool bracket = true,
-                             int phase = HALO_BOTH)
+// NCCL path / stand-alone calls: after a half-sweep of `colour` the freshly written
+// boundary planes go to the neighbours' halos as an explicit step
+static void halo_after_sweep(mgb_solver *s, Level &lv, int colour)
 {
     if (!lv.dist)
         return;
-    halo_step(s, lv, lv.a[MGB_U].base, 1 << colour, lv.own_hi - 1, lv.own_lo - 1, lv.own_lo,
-              lv.own_hi, bracket, phase);
+    halo_step(s, lv, lv.a[MGB_U].base, 1 << colour, lv.own_hi - 1, lv.own_hi - 2, lv.own_lo, 3);
 }
 
 static int fetch_scalar(mgb_solver *s, int slot, double *out)
@@ -1186,8 +1335,10 @@ extern "C" int mgb_sumsq(mgb_solver *s, int level, int which, double *sumsq)
         launch_sumsq(lv.a[which].base + first, n, lv.a[which].base + lv.g.cs + first, n,
                      s->partials, s->d_scal + 1, s->st);
     CKLAUNCH();
-    if (lv.dist)
+    if (lv.dist) {
         allreduce_scalar(s, 1);
+        close_epoch(s);
+    }
     if (nccl_status())
         return 1;
     return fetch_scalar(s, 1, sumsq);
@@ -1202,8 +1353,10 @@ extern "C" int mgb_error_sumsq(mgb_solver *s, double *sumsq)
     launch_error_sumsq(lv.g, lv.a[MGB_U].base, lv.h, lv.own_lo - lv.g.i0, lv.own_hi - lv.g.i0,
                        s->partials, s->d_scal + 2, s->st);
     CKLAUNCH();
-    if (lv.dist)
+    if (lv.dist) {
         allreduce_scalar(s, 2);
+        close_epoch(s);
+    }
     if (nccl_status())
         return 1;
     return fetch_scalar(s, 2, sumsq);
@@ -1218,39 +1371,20 @@ static void q_half_sweep(mgb_solver *s, int q, int colour, bool zero_guess = fal
         return;
     Level &lv = s->lv[q];
     const int lo = lv.sweep_lo(), hi = lv.sweep_hi();
-    if (zero_guess) {
+    // partitioned level, P2P path: the kernel itself waits for the neighbours' last sends
+    // and stores its boundary planes into their halos (halo.cuh)
+    HaloCtl h = make_ctl(s, lv);
+    if (h.epoch)
+        add_sweep_push(s, q, colour, h);
+    const HaloCtl *hp = h.epoch ? &h : nullptr;
+    if (zero_guess)
         launch_first_sweep_zero(lv.g, lv.a[MGB_U].base, lv.a[MGB_D].base, lv.hSq, colour, lo, hi,
-                                s->st);
-        halo_after_sweep(s, lv, colour);
-        return;
-    }
-    // worth it only where the interior of the sweep outlasts the exchange by far:
-    // >= 4M points per slab (off by default: MGB_OVERLAP=1)
-    if (lv.dist && s->opt_overlap && hi - lo >= 4 &&
-        (long long)(hi - lo) * lv.g.nj * lv.g.nk >= (4LL << 20)) {
-        // the two planes the neighbours are waiting for first; their exchange then
-        // runs on the communication stream underneath the interior of the sweep
-        // (within a colour the order of the updates does not matter)
-        launch_half_sweep(lv.g, lv.a[MGB_U].base, lv.a[MGB_D].base, lv.hSq, colour, lo, lo + 1,
-                          s->st);
-        launch_half_sweep(lv.g, lv.a[MGB_U].base, lv.a[MGB_D].base, lv.hSq, colour, hi - 1, hi,
-                          s->st);
-        if (s->opt_p2p) {
-            halo_after_sweep(s, lv, colour, false, HALO_PUSH);
-            launch_half_sweep(lv.g, lv.a[MGB_U].base, lv.a[MGB_D].base, lv.hSq, colour, lo + 1,
-                              hi - 1, s->st);
-            halo_after_sweep(s, lv, colour, false, HALO_WAIT);
-            return;
-        }
-        comm_begin(s);
-        halo_after_sweep(s, lv, colour, false);
-        launch_half_sweep(lv.g, lv.a[MGB_U].base, lv.a[MGB_D].base, lv.hSq, colour, lo + 1,
-                          hi - 1, s->st);
-        comm_end(s);
-        return;
-    }
-    launch_half_sweep(lv.g, lv.a[MGB_U].base, lv.a[MGB_D].base, lv.hSq, colour, lo, hi, s->st);
-    halo_after_sweep(s, lv, colour);
+                                s->st, hp);
+    else
+        launch_half_sweep(lv.g, lv.a[MGB_U].base, lv.a[MGB_D].base, lv.hSq, colour, lo, hi, s->st,
+                          hp);
+    if (lv.dist && !s->opt_p2p)
+        halo_after_sweep(s, lv, colour);  // NCCL path: an explicit exchange
 }
 
 static void q_smooth(mgb_solver *s, int q, int iters, int first_red, bool zero_guess = false)
@@ -1268,12 +1402,15 @@ static void q_residual(mgb_solver *s, int q, bool store, int slot)
         cudaMemsetAsync(s->d_scal + slot, 0, sizeof(double), s->st);
         return;
     }
+    const HaloCtl h = make_ctl(s, lv);  // reads the nearest halo plane on each side
+    const HaloCtl *hp = h.epoch ? &h : nullptr;
     if (store ||
         !launch_tile_residual(lv.g, lv.a[MGB_U].base, lv.a[MGB_D].base, lv.hSq, lv.invHsq, -1,
-                              lv.sweep_lo(), lv.sweep_hi(), s->partials, s->d_scal + slot, s->st))
+                              lv.sweep_lo(), lv.sweep_hi(), s->partials, s->d_scal + slot, s->st,
+                              hp))
         launch_residual(lv.g, lv.a[MGB_U].base, lv.a[MGB_D].base,
                         store ? lv.a[MGB_R].base : nullptr, lv.invHsq, lv.sweep_lo(),
-                        lv.sweep_hi(), s->partials, s->d_scal + slot, s->st);
+                        lv.sweep_hi(), s->partials, s->d_scal + slot, s->st, hp);
     if (lv.dist)
         allreduce_scalar(s, slot);
 }
@@ -1299,9 +1436,38 @@ static void q_restrict(mgb_solver *s, int q)
     launch_restrict(f.g, f.a[MGB_R].base, c.g, c.a[MGB_D].base, 0, c.g.li, s->st);
 }
 
-// residual + restriction; colour >= 0: the half-sweep of that colour is fused
-// in front (single-GPU levels; elsewhere it runs as its own kernel first)
-static void q_residual_restrict(mgb_solver *s, int q, int colour = -1)
+// all-gather of level qc's right-hand side (the first replicated level): every rank has
+// computed the coarse planes [Ilo, Ihi) and needs everybody else's (P2P path)
+static void q_gather_rhs(mgb_solver *s, int qc, int Ilo, int Ihi)
+{
+    Level &c = s->lv[qc];
+    GatherHost g{};
+    g.me = s->rank;
+    g.nranks = s->nranks;
+    for (int col = 0; col < 2; col++) {
+        g.src[col] = c.a[MGB_D].base + (long long)col * c.g.cs + (long long)Ilo * c.g.pj;
+        g.n[col] = (long long)(Ihi - Ilo) * c.g.pj;
+    }
+    for (int r = 0; r < s->nranks; r++) {
+        if (r == s->rank)
+            continue;
+        for (int col = 0; col < 2; col++)  // level qc has the same (whole) geometry everywhere
+            g.dst[r][col] = s->peers[r].d_coarse + (long long)col * c.g.cs + (long long)Ilo * c.g.pj;
+        g.peer_xf[r] = s->peers[r].xf;
+    }
+    g.my_xf = s->xflags;
+    g.off = ++s->n_gather;
+    g.timeout_ns = s->halo_timeout_ns;
+    g.err = s->d_halo_err;
+    launch_gather(g, s->st);
+    s->nccl_calls++;
+}
+
+// residual + restriction; colour >= 0: the half-sweep of that colour is fused in front
+// (single-GPU levels; elsewhere it runs as its own kernel first).  `fresh_halos`: the
+// caller knows that both colours of the two lower halo planes are current (inside the
+// cycle every half-sweep pushes its colour of planes own_hi-2 and own_hi-1).
+static void q_residual_restrict(mgb_solver *s, int q, int colour = -1, bool fresh_halos = false)
 {
     if (!s->works_on(q))
         return;
@@ -1321,21 +1487,29 @@ static void q_residual_restrict(mgb_solver *s, int q, int colour = -1)
     }
     if (colour >= 0)
         q_half_sweep(s, q, colour);
-    // the residual on plane own_lo-1 (needed by my first coarse plane) reads
-    // the solution on own_lo-2: fetch that plane, both colours
-    halo_step(s, f, f.a[MGB_U].base, 3, f.own_hi - 2, f.own_lo - 2, -1, -1);
+    // the residual on plane own_lo-1 (needed by my first coarse plane) reads the solution
+    // on own_lo-2 .. own_lo and the rhs on own_lo-1
+    if (!fresh_halos || !s->opt_p2p)
+        halo_step(s, f, f.a[MGB_U].base, 3, f.own_hi - 1, f.own_hi - 2, f.own_lo, 3);
     // my share of the coarse planes: those whose fine plane 2I I own
     int Ilo, Ihi;
     mgb_plan_slab(c.g.ni, s->nranks, s->rank, &Ilo, &Ihi);
+    HaloCtl h = make_ctl(s, f);
+    if (h.epoch && c.dist)
+        add_coarse_rhs_push(s, q - 1, h);
+    const HaloCtl *hp = h.epoch ? &h : nullptr;
     if (!launch_tile_residual_restrict(f.g, f.a[MGB_U].base, f.a[MGB_D].base, f.hSq, f.invHsq, -1,
-                                       c.g, c.a[MGB_D].base, Ilo - c.g.i0, Ihi - c.g.i0, s->st))
+                                       c.g, c.a[MGB_D].base, Ilo - c.g.i0, Ihi - c.g.i0, s->st, hp))
         launch_residual_restrict(f.g, f.a[MGB_U].base, f.a[MGB_D].base, f.invHsq, c.g,
-                                 c.a[MGB_D].base, Ilo - c.g.i0, Ihi - c.g.i0, s->st);
+                                 c.a[MGB_D].base, Ilo - c.g.i0, Ihi - c.g.i0, s->st, hp);
     if (c.dist) {
         // the coarse rhs on plane own_lo-1 feeds the next restriction
-        halo_step(s, c, c.a[MGB_D].base, 3, c.own_hi - 1, c.own_lo - 1, -1, -1);
+        if (!s->opt_p2p)
+            halo_step(s, c, c.a[MGB_D].base, 3, c.own_hi - 1, -1, -1, 1);
+    } else if (s->replicate) {
+        q_gather_rhs(s, q - 1, Ilo, Ihi);
     } else {
-        // agglomeration: gather the coarse rhs slabs on rank 0
+        // agglomeration (NCCL path): gather the coarse rhs slabs on rank 0
         comm_begin(s);
         NC(nccl().GroupStart());
         for (int col = 0; col < 2; col++) {
@@ -1377,11 +1551,14 @@ static void q_prolong(mgb_solver *s, int q, bool red_only = false)
         return;
     }
     // owned planes plus the nearest halo plane on each side: the neighbours
-    // compute the identical values, so no exchange is needed afterwards
+    // compute the identical values, so no exchange is needed afterwards.  The coarse
+    // planes read at the ends of the slab are halo planes of the coarse level (if that one
+    // is partitioned): its last sweeps pushed them
     const int lo = f.own_lo - (s->rank > 0 ? 1 : 0);
     const int hi = f.own_hi + (s->rank < s->nranks - 1 ? 1 : 0);
+    const HaloCtl h = make_ctl(s, c.dist ? c : f);
     launch_prolong_correct(c.g, c.a[MGB_U].base, f.g, f.a[MGB_U].base, lo - f.g.i0,
-                           hi - f.g.i0, s->st, cmask);
+                           hi - f.g.i0, s->st, cmask, (h.epoch && c.dist) ? &h : nullptr);
     if (red_only) {
         // only red entries of my halo planes were written, and the neighbours' next
         // push into them is BLACK: no fence needed
@@ -1397,6 +1574,8 @@ static void q_prolong(mgb_solver *s, int q, bool red_only = false)
 // correction of level LD-1 (a small grid) for the prolongation
 static void q_broadcast_agglomerated(mgb_solver *s)
 {
+    if (s->replicate)
+        return;  // every rank has computed level LD-1 itself
     Level &c = s->lv[s->LD - 1];
     comm_begin(s);
     NC(nccl().Broadcast(c.a[MGB_U].base, c.a[MGB_U].base, (size_t)(2 * c.g.cs), ncclDouble, 0,
@@ -1420,7 +1599,8 @@ static void q_coarse_solve(mgb_solver *s)
         return 1;                                                                 \
     if ((level_expr) < (min_level) || (level_expr) >= s->L)                       \
         return fail("level %d out of range [%d,%d)", (level_expr), (min_level), s->L); \
-    LaunchScope ls(s)
+    LaunchScope ls(s);                                                            \
+    Collective epoch_scope(s)
 
 extern "C" int mgb_half_sweep(mgb_solver *s, int level, int colour)
 {
@@ -1629,7 +1809,7 @@ static void enqueue_cycle(mgb_solver *s, int q, bool timed, int entry = -1)
     }
     if (s->opt_fuse) {
         StageTimer t(s, timed, q, MGB_ST_RESID1);  // 1294 + 1310 in one pass
-        q_residual_restrict(s, q, fuse_sweep ? 0 : -1);
+        q_residual_restrict(s, q, fuse_sweep ? 0 : -1, s->gs >= 1);
         s->calls[(size_t)q * MGB_NUM_STAGES + MGB_ST_RESTRICT]++;
     } else {
         {
@@ -1679,6 +1859,7 @@ static int build_graph(mgb_solver *s)
     const long long before = launches_issued();
     CK(cudaStreamBeginCapture(s->st, cudaStreamCaptureModeThreadLocal));
     enqueue_cycle(s, s->L - 1, false);
+    close_epoch(s);  // the graph's last node: every replay is one epoch of the halo protocol
     cudaError_t e = cudaStreamEndCapture(s->st, &graph);
     s->calls = saved;  // capture is not a cycle
     s->graph_launches = launches_issued() - before;
@@ -1715,6 +1896,7 @@ extern "C" int mgb_vcycle(mgb_solver *s, double *sumsq)
     if (s->coarse_dirty) {
         // direct array / operator calls may have left non-zero values on the faces of
         // coarse u arrays; the cycle (which no longer zeroes them every time) needs 0
+        Collective scope(s);
         for (int q = 0; q < s->L - 1; q++) {
             Level &lv = s->lv[q];
             if (!s->works_on(q))
@@ -1730,6 +1912,7 @@ extern "C" int mgb_vcycle(mgb_solver *s, double *sumsq)
         s->ev_used = 0;
         s->marks.clear();
         enqueue_cycle(s, s->L - 1, true);
+        close_epoch(s);
         s->launches += launches_issued() - before;
         CKLAUNCH();
         if (nccl_status())
@@ -1758,6 +1941,7 @@ extern "C" int mgb_vcycle(mgb_solver *s, double *sumsq)
         const long long before = launches_issued();
         std::vector<int> saved = s->calls;
         enqueue_cycle(s, s->L - 1, false);
+        close_epoch(s);
         s->calls = saved;
         s->launches += launches_issued() - before;
         CKLAUNCH();
@@ -1812,6 +1996,7 @@ extern "C" int mgb_fmg_init(mgb_solver *s, double *sumsq)
     }
     s->calls = saved;
     s->coarse_dirty = false;  // every coarse u was zeroed on the way up; the cycles keep faces 0
+    close_epoch(s);
     CKLAUNCH();
     if (nccl_status())
         return 1;

@@ -352,75 +352,89 @@ k_half_sweep(Geo g, const double *__restrict__ vo, double *__restrict__ vc,
 // unrolled by two so that no in-flight value is ever copied).  Twice the bytes
 // in flight per thread; the j+-1 rows and the k neighbour still come through
 // L1/L2 at the point of use.
-template <int COLOUR>
-__global__ void __launch_bounds__(256)
+// HALO = false: the single-GPU instantiation carries none of the exchange code
+template <int COLOUR, bool HALO>
+__global__ void __launch_bounds__(256, 4)
 k_half_sweep_pipe(Geo g, const double *__restrict__ vo, double *__restrict__ vc,
-                  const double *__restrict__ dc, double hSq, int il_lo, int il_hi, int chunk)
+                  const double *__restrict__ dc, double hSq, int il_lo, int il_hi, int chunk,
+                  const HaloCtl h)
 {
     const int npair = g.kh >> 1;
     const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (q >= (g.pj >> 1))
-        return;
-    const int j = (int)(q / npair);
-    if (j < 1 || j > g.nj - 2)
-        return;
-    const int mp = (int)(q - (long long)j * npair);
     const int ia = il_lo + blockIdx.y * chunk;
     const int ib = min(ia + chunk, il_hi);
     if (ia >= ib)
-        return;
-    const long long off = 2 * q;
-    const double sixth = 1. / 6;
-    const int kh = g.kh;
-    const int kmax = g.nk - 2;
-    const long long pj = g.pj;
+        return;  // whole block
+    // partitioned level: the first / last chunk of the slab reads a halo plane
+    if (HALO)
+        halo_wait_cta(h, ia == il_lo, ib == il_hi);
+    const int j = (int)(q / npair);
+    const bool active = q < (g.pj >> 1) && j >= 1 && j <= g.nj - 2;
+    const bool pushes = HALO && h.epoch && (halo_takes_part(h.push_up, ia, ib) ||
+                                            halo_takes_part(h.push_low, ia, ib));
+    if (active) {
+        const int mp = (int)(q - (long long)j * npair);
+        const long long off = 2 * q;
+        const double sixth = 1. / 6;
+        const int kh = g.kh;
+        const int kmax = g.nk - 2;
+        const long long pj = g.pj;
 
-    const double *po = vo + (long long)ia * pj + off;  // own pair, other colour, plane il
-    const double *pd = dc + (long long)ia * pj + off;  // rhs of this colour, plane il
-    double *pc = vc + (long long)ia * pj + off;
-    double2 bot = ld2(po - pj);
-    double2 mid = ld2(po);
-    struct Pre { double2 top, dd; };
-    Pre A, B;
-    A.top = ld2(po + pj);
-    A.dd = ld2(pd);
-    B = A;
-    int kp = (COLOUR ^ (g.i0 + ia + j)) & 1;
-    int il = ia;
-    auto step = [&](const Pre &cur, Pre &nxt) {
-        if (il + 1 < ib) {
-            nxt.top = ld2(po + 2 * pj);
-            nxt.dd = ld2(pd + pj);
+        const double *po = vo + (long long)ia * pj + off;  // own pair, other colour, plane il
+        const double *pd = dc + (long long)ia * pj + off;  // rhs of this colour, plane il
+        double *pc = vc + (long long)ia * pj + off;
+        double2 bot = ld2(po - pj);
+        double2 mid = ld2(po);
+        struct Pre { double2 top, dd; };
+        Pre A, B;
+        A.top = ld2(po + pj);
+        A.dd = ld2(pd);
+        B = A;
+        int kp = (COLOUR ^ (g.i0 + ia + j)) & 1;
+        int il = ia;
+        auto step = [&](const Pre &cur, Pre &nxt) {
+            if (il + 1 < ib) {
+                nxt.top = ld2(po + 2 * pj);
+                nxt.dd = ld2(pd + pj);
+            }
+            const double2 jm = ld2(po - kh);
+            const double2 jp = ld2(po + kh);
+            double a0, a1, a2;
+            if (kp) {
+                a0 = mid.x; a1 = mid.y; a2 = po[2];
+            } else {
+                a0 = po[-1]; a1 = mid.x; a2 = mid.y;
+            }
+            const double r0 = gs_point(bot.x, cur.top.x, jm.x, jp.x, a0, a1, hSq, cur.dd.x, sixth);
+            const double r1 = gs_point(bot.y, cur.top.y, jm.y, jp.y, a1, a2, hSq, cur.dd.y, sixth);
+            const int k0 = 4 * mp + kp, k1 = k0 + 2;
+            const bool ok0 = k0 >= 1 && k0 <= kmax;
+            const bool ok1 = k1 <= kmax;  // k1 >= 2 always
+            if (ok0 && ok1)
+                st2(pc, r0, r1);
+            else if (ok0)
+                pc[0] = r0;
+            else if (ok1)
+                pc[1] = r1;
+            if (pushes)  // boundary plane of the slab: the same store, into the peer's halo
+                halo_mirror_pair(h, il, off, ok0, ok1, r0, r1);
+            bot = mid;
+            mid = cur.top;  // already consumed above: the copy does not wait
+            po += pj; pd += pj; pc += pj;
+            kp ^= 1;
+            il++;
+        };
+        while (il < ib) {
+            step(A, B);
+            if (il < ib)
+                step(B, A);
         }
-        const double2 jm = ld2(po - kh);
-        const double2 jp = ld2(po + kh);
-        double a0, a1, a2;
-        if (kp) {
-            a0 = mid.x; a1 = mid.y; a2 = po[2];
-        } else {
-            a0 = po[-1]; a1 = mid.x; a2 = mid.y;
-        }
-        const double r0 = gs_point(bot.x, cur.top.x, jm.x, jp.x, a0, a1, hSq, cur.dd.x, sixth);
-        const double r1 = gs_point(bot.y, cur.top.y, jm.y, jp.y, a1, a2, hSq, cur.dd.y, sixth);
-        const int k0 = 4 * mp + kp, k1 = k0 + 2;
-        const bool ok0 = k0 >= 1 && k0 <= kmax;
-        const bool ok1 = k1 <= kmax;  // k1 >= 2 always
-        if (ok0 && ok1)
-            st2(pc, r0, r1);
-        else if (ok0)
-            pc[0] = r0;
-        else if (ok1)
-            pc[1] = r1;
-        bot = mid;
-        mid = cur.top;  // already consumed above: the copy does not wait
-        po += pj; pd += pj; pc += pj;
-        kp ^= 1;
-        il++;
-    };
-    while (il < ib) {
-        step(A, B);
-        if (il < ib)
-            step(B, A);
+    }
+    if (pushes) {
+        if (halo_takes_part(h.push_up, ia, ib))
+            halo_signal_cta(h, h.push_up);
+        if (halo_takes_part(h.push_low, ia, ib))
+            halo_signal_cta(h, h.push_low);
     }
 }
 
@@ -432,66 +446,88 @@ k_half_sweep_pipe(Geo g, const double *__restrict__ vo, double *__restrict__ vc,
 template <int COLOUR>
 __global__ void __launch_bounds__(256)
 k_first_sweep_zero(Geo g, double *__restrict__ vc, const double *__restrict__ dc, double hSq,
-                   int il_lo, int il_hi)
+                   int il_lo, int il_hi, const HaloCtl h)
 {
     const int npair = g.kh >> 1;
     const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (q >= (g.pj >> 1))
-        return;
-    const int j = (int)(q / npair);
-    if (j < 1 || j > g.nj - 2)
-        return;
-    const int mp = (int)(q - (long long)j * npair);
     const int il = il_lo + blockIdx.y;
     if (il >= il_hi)
-        return;
-    const long long idx = (long long)il * g.pj + 2 * q;
-    const double2 dd = ld2(dc + idx);
-    const double sixth = 1. / 6;
-    const double r0 = gs_point(0., 0., 0., 0., 0., 0., hSq, dd.x, sixth);
-    const double r1 = gs_point(0., 0., 0., 0., 0., 0., hSq, dd.y, sixth);
-    const int kp = (COLOUR ^ (g.i0 + il + j)) & 1;
-    const int k0 = 4 * mp + kp, k1 = k0 + 2, kmax = g.nk - 2;
-    const bool ok0 = k0 >= 1 && k0 <= kmax, ok1 = k1 <= kmax;
-    if (ok0 && ok1)
-        st2(vc + idx, r0, r1);
-    else if (ok0)
-        vc[idx] = r0;
-    else if (ok1)
-        vc[idx + 1] = r1;
+        return;  // whole block
+    const int j = (int)(q / npair);
+    if (q < (g.pj >> 1) && j >= 1 && j <= g.nj - 2) {
+        const int mp = (int)(q - (long long)j * npair);
+        const long long idx = (long long)il * g.pj + 2 * q;
+        const double2 dd = ld2(dc + idx);
+        const double sixth = 1. / 6;
+        const double r0 = gs_point(0., 0., 0., 0., 0., 0., hSq, dd.x, sixth);
+        const double r1 = gs_point(0., 0., 0., 0., 0., 0., hSq, dd.y, sixth);
+        const int kp = (COLOUR ^ (g.i0 + il + j)) & 1;
+        const int k0 = 4 * mp + kp, k1 = k0 + 2, kmax = g.nk - 2;
+        const bool ok0 = k0 >= 1 && k0 <= kmax, ok1 = k1 <= kmax;
+        if (ok0 && ok1)
+            st2(vc + idx, r0, r1);
+        else if (ok0)
+            vc[idx] = r0;
+        else if (ok1)
+            vc[idx + 1] = r1;
+        if (h.epoch)  // reads the rhs only: nothing to wait for, but the result travels
+            halo_mirror_pair(h, il, 2 * q, ok0, ok1, r0, r1);
+    }
+    if (h.epoch) {
+        if (halo_takes_part(h.push_up, il, il + 1))
+            halo_signal_cta(h, h.push_up);
+        if (halo_takes_part(h.push_low, il, il + 1))
+            halo_signal_cta(h, h.push_low);
+    }
 }
 
 void launch_first_sweep_zero(const Geo &g, double *v, const double *d, double hSq, int colour,
-                             int il_lo, int il_hi, cudaStream_t st)
+                             int il_lo, int il_hi, cudaStream_t st, const HaloCtl *hp)
 {
     if (il_hi <= il_lo)
         return;
     const long long pairs = (long long)g.pj / 2;
     const dim3 grid((unsigned)((pairs + 255) / 256), (unsigned)(il_hi - il_lo));
+    HaloCtl h = hp ? *hp : HaloCtl{};
+    h.push_up.nblocks = halo_chunks_with(h.push_up, il_lo, il_hi, 1) * grid.x;
+    h.push_low.nblocks = halo_chunks_with(h.push_low, il_lo, il_hi, 1) * grid.x;
     if (colour)
-        k_first_sweep_zero<1><<<grid, 256, 0, st>>>(g, v + g.cs, d + g.cs, hSq, il_lo, il_hi);
+        k_first_sweep_zero<1><<<grid, 256, 0, st>>>(g, v + g.cs, d + g.cs, hSq, il_lo, il_hi, h);
     else
-        k_first_sweep_zero<0><<<grid, 256, 0, st>>>(g, v, d, hSq, il_lo, il_hi);
+        k_first_sweep_zero<0><<<grid, 256, 0, st>>>(g, v, d, hSq, il_lo, il_hi, h);
     COUNT_LAUNCH();
 }
 
 void launch_half_sweep(const Geo &g, double *v, const double *d, double hSq,
-                       int colour, int il_lo, int il_hi, cudaStream_t st)
+                       int colour, int il_lo, int il_hi, cudaStream_t st, const HaloCtl *hp)
 {
     if (il_hi <= il_lo)
         return;
-    if (launch_tile_half_sweep(g, v, d, hSq, colour, il_lo, il_hi, st))
+    if (launch_tile_half_sweep(g, v, d, hSq, colour, il_lo, il_hi, st, hp))
         return;
     static const int pipe = getenv("MGB_SWEEP_PIPE") ? atoi(getenv("MGB_SWEEP_PIPE")) : 1;
-    if (pipe) {
-        static const int occp = resident_blocks(k_half_sweep_pipe<1>, 256, 0);
-        const MarchCfg c = march_cfg(g, il_hi - il_lo, 256, occp);
-        if (colour)
-            k_half_sweep_pipe<1><<<c.grid, c.block, 0, st>>>(g, v, v + g.cs, d + g.cs, hSq, il_lo,
-                                                             il_hi, c.chunk);
-        else
-            k_half_sweep_pipe<0><<<c.grid, c.block, 0, st>>>(g, v + g.cs, v, d, hSq, il_lo, il_hi,
-                                                             c.chunk);
+    if (pipe || hp) {
+        static const int occp = resident_blocks(k_half_sweep_pipe<1, false>, 256, 0);
+        static const int occh = resident_blocks(k_half_sweep_pipe<1, true>, 256, 0);
+        const MarchCfg c = march_cfg(g, il_hi - il_lo, 256, hp ? occh : occp);
+        HaloCtl h = hp ? *hp : HaloCtl{};
+        h.push_up.nblocks = halo_chunks_with(h.push_up, il_lo, il_hi, c.chunk) * c.grid.x;
+        h.push_low.nblocks = halo_chunks_with(h.push_low, il_lo, il_hi, c.chunk) * c.grid.x;
+        if (hp) {
+            if (colour)
+                k_half_sweep_pipe<1, true><<<c.grid, c.block, 0, st>>>(g, v, v + g.cs, d + g.cs, hSq,
+                                                                       il_lo, il_hi, c.chunk, h);
+            else
+                k_half_sweep_pipe<0, true><<<c.grid, c.block, 0, st>>>(g, v + g.cs, v, d, hSq, il_lo,
+                                                                       il_hi, c.chunk, h);
+        } else {
+            if (colour)
+                k_half_sweep_pipe<1, false><<<c.grid, c.block, 0, st>>>(g, v, v + g.cs, d + g.cs, hSq,
+                                                                        il_lo, il_hi, c.chunk, h);
+            else
+                k_half_sweep_pipe<0, false><<<c.grid, c.block, 0, st>>>(g, v + g.cs, v, d, hSq, il_lo,
+                                                                        il_hi, c.chunk, h);
+        }
         COUNT_LAUNCH();
         return;
     }
@@ -514,7 +550,7 @@ template <bool STORE>
 __global__ void __launch_bounds__(256)
 k_residual(Geo g, const double *__restrict__ v, const double *__restrict__ d,
            double *__restrict__ r, double invHsq, int il_lo, int il_hi, int chunk,
-           double *__restrict__ partials)
+           double *__restrict__ partials, const HaloCtl h)
 {
     const int npair = g.kh >> 1;
     const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -522,6 +558,7 @@ k_residual(Geo g, const double *__restrict__ v, const double *__restrict__ d,
     const int j = (int)(q / npair);
     const int ia = il_lo + blockIdx.y * chunk;
     const int ib = min(ia + chunk, il_hi);
+    halo_wait_cta(h, ia < ib && ia == il_lo, ia < ib && ib == il_hi);
     if (q < (g.pj >> 1) && j >= 1 && j <= g.nj - 2 && ia < ib) {
         const int mp = (int)(q - (long long)j * npair);
         const long long off = 2 * q;
@@ -581,8 +618,9 @@ k_residual(Geo g, const double *__restrict__ v, const double *__restrict__ d,
 
 void launch_residual(const Geo &g, const double *v, const double *d, double *r,
                      double invHsq, int il_lo, int il_hi, double *partials,
-                     double *out_sumsq, cudaStream_t st)
+                     double *out_sumsq, cudaStream_t st, const HaloCtl *hp)
 {
+    const HaloCtl h = hp ? *hp : HaloCtl{};
     if (il_hi <= il_lo) {
         cudaMemsetAsync(out_sumsq, 0, sizeof(double), st);
         return;
@@ -595,10 +633,10 @@ void launch_residual(const Geo &g, const double *v, const double *d, double *r,
     }
     if (r)
         k_residual<true><<<c.grid, c.block, 0, st>>>(g, v, d, r, invHsq, il_lo, il_hi,
-                                                     c.chunk, partials);
+                                                     c.chunk, partials, h);
     else
         k_residual<false><<<c.grid, c.block, 0, st>>>(g, v, d, nullptr, invHsq, il_lo,
-                                                      il_hi, c.chunk, partials);
+                                                      il_hi, c.chunk, partials, h);
     COUNT_LAUNCH();
     k_finish_sum<<<1, 1024, 0, st>>>(partials, (int)(c.grid.x * c.grid.y), out_sumsq);
     COUNT_LAUNCH();
@@ -681,7 +719,7 @@ template <int MAXT>
 __global__ void __launch_bounds__(MAXT)
 k_residual_restrict(Geo gf, const double *__restrict__ v, const double *__restrict__ d,
                     double invHsq, Geo gc, double *__restrict__ dc, int Il_lo, int Il_hi,
-                    int chunk, int TY)
+                    int chunk, int TY, const HaloCtl h)
 {
     extern __shared__ double rs_all[];
     const int npair = gf.kh >> 1;
@@ -708,6 +746,8 @@ k_residual_restrict(Geo gf, const double *__restrict__ v, const double *__restri
     // interior coarse planes of this chunk (global index 1 .. ni-2)
     const int Im0 = max(Ia, 1 - gc.i0);
     const int Im1 = min(Ib, gc.ni - 1 - gc.i0);
+    // partitioned level: the chunks at the ends of the slab read fine halo planes
+    halo_wait_cta(h, Ia < Ib && Ia == Il_lo, Ia < Ib && Ib == Il_hi);
 
     // coarse boundary planes inside the chunk: zeros
     if (coarse_thr) {
@@ -806,6 +846,12 @@ k_residual_restrict(Geo gf, const double *__restrict__ v, const double *__restri
                     const long long row = ((long long)Il * gc.nj + J) * gc.kh;
                     if (K0in) dc[(long long)S * gc.cs + row + mp] = K0int ? a0 : 0.;
                     if (K1in) dc[(long long)(S ^ 1) * gc.cs + row + mp] = K1int ? a1 : 0.;
+                    // my last coarse plane is the upper neighbour's coarse-rhs halo
+                    if (h.push_up.peer_flag && Il == h.push_up.plane[0]) {
+                        const long long prow = (long long)J * gc.kh + mp;
+                        if (K0in) h.push_up.dst[S][prow] = K0int ? a0 : 0.;
+                        if (K1in) h.push_up.dst[S ^ 1][prow] = K1int ? a1 : 0.;
+                    }
                 }
                 acc0 = s0;  // ... and opens I+1
                 acc1 = s1;
@@ -817,11 +863,13 @@ k_residual_restrict(Geo gf, const double *__restrict__ v, const double *__restri
         }
         buf ^= 1;
     }
+    if (halo_takes_part(h.push_up, Ia, Ib))
+        halo_signal_cta(h, h.push_up);
 }
 
 void launch_residual_restrict(const Geo &gf, const double *vf, const double *df,
                               double invHsq, const Geo &gc, double *dc, int Il_lo,
-                              int Il_hi, cudaStream_t st)
+                              int Il_hi, cudaStream_t st, const HaloCtl *hp)
 {
     if (Il_hi <= Il_lo)
         return;
@@ -853,8 +901,10 @@ void launch_residual_restrict(const Geo &gf, const double *vf, const double *df,
     const int nch = pick_chunks(bx, nplanes, occ);
     const int chunk = (nplanes + nch - 1) / nch;
     const unsigned by = (nplanes + chunk - 1) / chunk;
+    HaloCtl h = hp ? *hp : HaloCtl{};
+    h.push_up.nblocks = halo_chunks_with(h.push_up, Il_lo, Il_hi, chunk) * bx;
     k_residual_restrict<1024><<<dim3(bx, by), threads, sh, st>>>(gf, vf, df, invHsq, gc, dc,
-                                                               Il_lo, Il_hi, chunk, TY);
+                                                               Il_lo, Il_hi, chunk, TY, h);
     COUNT_LAUNCH();
 }
 
@@ -987,16 +1037,18 @@ struct F8 {
 
 __global__ void __launch_bounds__(256, 2)
 k_prolong_correct8(Geo gc, const double *__restrict__ ec, Geo gf, double *ef, int il_lo,
-                   int il_hi, int chunk, int cmask)
+                   int il_hi, int chunk, int cmask, const HaloCtl h)
 {
     const int noct = gf.kh >> 2;
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int ia = il_lo + blockIdx.y * chunk;
+    const int ib = min(ia + chunk, il_hi);
+    // partitioned level: the coarse rows the ends of the slab read are halo planes
+    halo_wait_cta(h, ia < ib && ia == il_lo, ia < ib && ib == il_hi);
     if (t >= (long long)gf.nj * noct)
         return;
     const int j = (int)(t / noct);
     const int q = (int)(t - (long long)j * noct);
-    const int ia = il_lo + blockIdx.y * chunk;
-    const int ib = min(ia + chunk, il_hi);
     const int k0 = 8 * q;
     if (ia >= ib || k0 >= gf.nk)
         return;  // pad columns only
@@ -1167,14 +1219,21 @@ void launch_add_zero_faces(const Geo &g, double *a, int colour, int il_lo, int i
 }
 
 void launch_prolong_correct(const Geo &gc, const double *ec, const Geo &gf,
-                            double *ef, int il_lo, int il_hi, cudaStream_t st, int cmask)
+                            double *ef, int il_lo, int il_hi, cudaStream_t st, int cmask,
+                            const HaloCtl *hp)
 {
     if (il_hi <= il_lo)
         return;
-    if (launch_tile_prolong(gc, ec, gf, ef, il_lo, il_hi, cmask, st))
+    // the TMA ring kernel marches (even, odd) plane pairs: a range that starts on an odd
+    // global plane (a slab's lower halo plane) gets that one plane from the marching kernel
+    if (((gf.i0 + il_lo) & 1) && il_hi - il_lo > 8) {
+        launch_prolong_correct(gc, ec, gf, ef, il_lo, il_lo + 1, st, cmask, hp);
+        il_lo++;
+    }
+    if (launch_tile_prolong(gc, ec, gf, ef, il_lo, il_hi, cmask, st, hp))
         return;
     static const int wide = getenv("MGB_PROLONG_WIDE") ? atoi(getenv("MGB_PROLONG_WIDE")) : 1;
-    if (wide) {
+    if (wide || hp) {
         static const int occ8 = resident_blocks(k_prolong_correct8, 256, 0);
         const long long items = (long long)gf.nj * (gf.kh >> 2);
         const unsigned bx = (unsigned)((items + 255) / 256);
@@ -1184,7 +1243,7 @@ void launch_prolong_correct(const Geo &gc, const double *ec, const Geo &gf,
         chunk += chunk & 1;  // whole (even, odd) pairs per chunk
         const unsigned by = (unsigned)((nplanes + chunk - 1) / chunk);
         k_prolong_correct8<<<dim3(bx, by), 256, 0, st>>>(gc, ec, gf, ef, il_lo, il_hi, chunk,
-                                                         cmask);
+                                                         cmask, hp ? *hp : HaloCtl{});
         COUNT_LAUNCH();
         return;
     }
@@ -1195,20 +1254,23 @@ void launch_prolong_correct(const Geo &gc, const double *ec, const Geo &gf,
 }
 
 // ----------------------------------------------------------------------------
-// halo exchange over NVLink: P2P stores into the neighbour's halo planes + a
-// sequence-numbered flag (release/acquire at system scope).  One process per
-// GPU, the neighbour's arrays mapped through CUDA IPC.
+// Multi-GPU plumbing that is NOT fused into a compute kernel (halo.cuh has the
+// fused part): explicit halo steps (uploads, fences, the odd stand-alone call),
+// the all-gather of the first replicated level, the exchange of norm partials,
+// and the kernel that closes an epoch.  One process per GPU; peers' memory is
+// mapped through CUDA IPC and written with plain stores over NVLink.
 // ----------------------------------------------------------------------------
-struct HaloDir {  // one direction of a halo step: up to two runs + the neighbour's flag
-    const double *src[2];
-    double *dst[2];
-    long long n[2];
+struct HaloDir {  // one direction of an explicit halo step: up to four runs + the flag
+    const double *src[4];
+    double *dst[4];
+    long long n[4];
     unsigned long long *peer_flag;  // nullptr: nothing goes this way
-    unsigned long long *seq;        // my sequence number for this direction (local)
-    unsigned int *done;             // block counter (local)
+    unsigned int *count;            // local arrival counter
+    unsigned long long off;         // sequence offset within the epoch
 };
 
-__global__ void __launch_bounds__(256) k_halo_push(HaloDir up, HaloDir low)
+__global__ void __launch_bounds__(256)
+k_halo_push(HaloDir up, HaloDir low, const unsigned long long *epoch)
 {
     // the first gridDim.x/2 blocks (or all, if only one direction is active)
     // serve `up`, the rest `low`
@@ -1222,7 +1284,7 @@ __global__ void __launch_bounds__(256) k_halo_push(HaloDir up, HaloDir low)
     const long long t0 = (long long)b * blockDim.x + threadIdx.x;
     // runs start on 16-byte boundaries and have even lengths (colour planes)
 #pragma unroll
-    for (int k = 0; k < 2; k++) {
+    for (int k = 0; k < 4; k++) {
         const double2 *s = reinterpret_cast<const double2 *>(d.src[k]);
         double2 *o = reinterpret_cast<double2 *>(d.dst[k]);
         for (long long t = t0; 2 * t < d.n[k]; t += stride)
@@ -1231,58 +1293,118 @@ __global__ void __launch_bounds__(256) k_halo_push(HaloDir up, HaloDir low)
     __threadfence_system();  // this thread's peer stores are visible system-wide ...
     __syncthreads();
     if (threadIdx.x == 0) {
-        const unsigned int prev = atomicAdd(d.done, 1u);
+        const unsigned int prev = atomicAdd(d.count, 1u);
         if (prev == nb - 1) {  // ... and the last block to get here has seen all of them
-            *d.done = 0;
-            const unsigned long long v = *d.seq + 1;
-            *d.seq = v;
+            *d.count = 0;
             __threadfence_system();
-            asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(d.peer_flag), "l"(v)
-                         : "memory");
+            halo_st_release(d.peer_flag, *epoch * kHaloEpochStride + d.off);
         }
     }
 }
 
-__device__ __forceinline__ unsigned long long global_ns()
+// thread 0 waits for the lower side, thread 1 for the upper one
+__global__ void k_halo_wait(HaloCtl h)
 {
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-    return t;
+    if (threadIdx.x == 0)
+        halo_wait_one(h, h.wait_low, 1u);
+    else if (threadIdx.x == 1)
+        halo_wait_one(h, h.wait_up, 2u);
 }
 
-// thread 0 waits for flag0 (if any), thread 1 for flag1 (if any).  A neighbour
-// that never shows up must not hang the GPU for ever, nor poison the context
-// with a trap: after `timeout_ns` (wall clock, %globaltimer; 0 = wait for ever)
-// the waiter records which side it gave up on in *err (pinned host memory, read
-// by the host after the next synchronisation) and lets the stream go on.
-__global__ void k_halo_wait(const unsigned long long *flag0, unsigned long long *expect0,
-                            const unsigned long long *flag1, unsigned long long *expect1,
-                            unsigned long long timeout_ns, unsigned int *err)
+// end of a collective operation: remember the last sends of this epoch (a wait issued
+// before the first send of a later epoch refers to them), open the next epoch
+__global__ void k_epoch_close(unsigned long long *xf, unsigned long long n_up,
+                              unsigned long long n_low)
 {
-    const unsigned long long *flag = threadIdx.x == 0 ? flag0 : flag1;
-    unsigned long long *expect = threadIdx.x == 0 ? expect0 : expect1;
-    if (!flag)
-        return;
-    const unsigned long long v = *expect + 1;
-    *expect = v;
-    const unsigned long long t0 = global_ns();
-    unsigned int spins = 0;
-    while (true) {
-        unsigned long long cur;
-        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(cur) : "l"(flag) : "memory");
-        if (cur >= v)
-            break;
-        if (timeout_ns && (++spins & 1023u) == 0 && global_ns() - t0 > timeout_ns) {
-            if (err) {
-                atomicOr_system(err, 1u << threadIdx.x);
-                __threadfence_system();
-            }
-            break;
-        }
+    const unsigned long long e = xf[XF_EPOCH];
+    if (n_up)
+        xf[XF_PREV_UP] = e * kHaloEpochStride + n_up;
+    if (n_low)
+        xf[XF_PREV_LOW] = e * kHaloEpochStride + n_low;
+    xf[XF_EPOCH] = e + 1;
+}
+
+// All-gather of the first replicated level's right-hand side: every rank has computed
+// its slab of coarse planes (two runs: one per colour) and needs everybody else's.
+// Block b talks to one peer: "I am done reading the old contents" -> wait for the same
+// from the peer -> copy my slab into the peer's array -> "your copy of my slab is
+// complete" -> wait for the peer's slab here.  Pushes come before waits on every rank,
+// so the pairwise handshakes cannot deadlock.
+struct GatherArg {
+    int me, nranks;
+    const double *src[2];
+    long long n[2];                       // doubles per run (even, 16-byte aligned)
+    double *dst[kMaxRanks][2];            // [peer][run]
+    unsigned long long *peer_xf[kMaxRanks];
+    unsigned long long *my_xf;
+    unsigned long long off;               // sequence offset of this gather within the epoch
+    unsigned long long timeout_ns;
+    unsigned int *err;
+};
+
+__global__ void __launch_bounds__(256) k_gather(const GatherArg a)
+{
+    int peer = blockIdx.x;
+    if (peer >= a.me)
+        peer++;
+    const unsigned long long v = a.my_xf[XF_EPOCH] * kHaloEpochStride + a.off;
+    if (threadIdx.x == 0) {
+        halo_st_release(a.peer_xf[peer] + XF_READY + a.me, v);
+        halo_spin(a.my_xf + XF_READY + peer, v, a.timeout_ns, a.err, 4u);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+        const double2 *s = reinterpret_cast<const double2 *>(a.src[k]);
+        double2 *o = reinterpret_cast<double2 *>(a.dst[peer][k]);
+        for (long long t = threadIdx.x; 2 * t < a.n[k]; t += blockDim.x)
+            o[t] = s[t];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        halo_st_release(a.peer_xf[peer] + XF_DATA + a.me, v);
+        halo_spin(a.my_xf + XF_DATA + peer, v, a.timeout_ns, a.err, 4u);
     }
 }
 
-void launch_halo_push(const HaloRun &up, const HaloRun &low, cudaStream_t st)
+// Sum of one device scalar over the ranks, in RANK ORDER on every rank (bitwise the same
+// everywhere and from run to run): thread p hands my partial to peer p and waits for its.
+struct NormArg {
+    int me, nranks;
+    double *scalar;                        // in: my partial, out: the sum
+    unsigned long long *peer_xf[kMaxRanks];
+    unsigned long long *my_xf;
+    unsigned long long off;
+    unsigned long long timeout_ns;
+    unsigned int *err;
+};
+
+__global__ void k_norm_exchange(const NormArg a)
+{
+    const int p = threadIdx.x;
+    const unsigned long long e = a.my_xf[XF_EPOCH];
+    const unsigned long long v = e * kHaloEpochStride + a.off;
+    const int slot = XF_NORMPART + (int)((e + a.off) & 1) * kMaxRanks;  // alternate buffers
+    if (p < a.nranks && p != a.me) {
+        double *parts = reinterpret_cast<double *>(a.peer_xf[p] + slot);
+        parts[a.me] = *a.scalar;
+        __threadfence_system();
+        halo_st_release(a.peer_xf[p] + XF_NORMFLAG + a.me, v);
+        halo_spin(a.my_xf + XF_NORMFLAG + p, v, a.timeout_ns, a.err, 8u);
+    }
+    __syncthreads();
+    if (p == 0) {
+        const double *parts = reinterpret_cast<const double *>(a.my_xf + slot);
+        double sum = 0.;
+        for (int r = 0; r < a.nranks; r++)
+            sum = __dadd_rn(sum, r == a.me ? *a.scalar : parts[r]);
+        *a.scalar = sum;
+    }
+}
+
+void launch_halo_push(const HaloRun &up, const HaloRun &low, const unsigned long long *epoch,
+                      cudaStream_t st)
 {
     if (!up.peer_flag && !low.peer_flag)
         return;
@@ -1291,7 +1413,7 @@ void launch_halo_push(const HaloRun &up, const HaloRun &low, cudaStream_t st)
     const HaloRun *in[2] = {&up, &low};
     HaloDir *out[2] = {&a, &b};
     for (int i = 0; i < 2; i++) {
-        for (int k = 0; k < 2; k++) {
+        for (int k = 0; k < 4; k++) {
             out[i]->src[k] = in[i]->src[k];
             out[i]->dst[k] = in[i]->dst[k];
             out[i]->n[k] = in[i]->n[k];
@@ -1299,8 +1421,8 @@ void launch_halo_push(const HaloRun &up, const HaloRun &low, cudaStream_t st)
                 most = in[i]->n[k];
         }
         out[i]->peer_flag = in[i]->peer_flag;
-        out[i]->seq = in[i]->seq;
-        out[i]->done = in[i]->done;
+        out[i]->count = in[i]->count;
+        out[i]->off = in[i]->off;
     }
     long long nb = (most / 2 + 256 * 8 - 1) / (256 * 8);  // ~8 x 16 B per thread and direction
     if (nb > 64)
@@ -1309,17 +1431,60 @@ void launch_halo_push(const HaloRun &up, const HaloRun &low, cudaStream_t st)
         nb = 1;
     if (up.peer_flag && low.peer_flag)
         nb *= 2;
-    k_halo_push<<<(unsigned)nb, 256, 0, st>>>(a, b);
+    k_halo_push<<<(unsigned)nb, 256, 0, st>>>(a, b, epoch);
     COUNT_LAUNCH();
 }
 
-void launch_halo_wait(const unsigned long long *flag0, unsigned long long *expect0,
-                      const unsigned long long *flag1, unsigned long long *expect1,
-                      unsigned long long timeout_ns, unsigned int *err, cudaStream_t st)
+void launch_halo_wait(const HaloCtl &h, cudaStream_t st)
 {
-    if (!flag0 && !flag1)
+    if (!h.epoch || (!h.wait_low.flag && !h.wait_up.flag))
         return;
-    k_halo_wait<<<1, 2, 0, st>>>(flag0, expect0, flag1, expect1, timeout_ns, err);
+    k_halo_wait<<<1, 2, 0, st>>>(h);
+    COUNT_LAUNCH();
+}
+
+void launch_epoch_close(unsigned long long *xf, unsigned long long n_up, unsigned long long n_low,
+                        cudaStream_t st)
+{
+    k_epoch_close<<<1, 1, 0, st>>>(xf, n_up, n_low);
+    COUNT_LAUNCH();
+}
+
+void launch_gather(const GatherHost &g, cudaStream_t st)
+{
+    GatherArg a{};
+    a.me = g.me;
+    a.nranks = g.nranks;
+    for (int k = 0; k < 2; k++) {
+        a.src[k] = g.src[k];
+        a.n[k] = g.n[k];
+    }
+    for (int r = 0; r < g.nranks && r < kMaxRanks; r++) {
+        a.dst[r][0] = g.dst[r][0];
+        a.dst[r][1] = g.dst[r][1];
+        a.peer_xf[r] = g.peer_xf[r];
+    }
+    a.my_xf = g.my_xf;
+    a.off = g.off;
+    a.timeout_ns = g.timeout_ns;
+    a.err = g.err;
+    k_gather<<<g.nranks - 1, 256, 0, st>>>(a);
+    COUNT_LAUNCH();
+}
+
+void launch_norm_exchange(const NormHost &g, cudaStream_t st)
+{
+    NormArg a{};
+    a.me = g.me;
+    a.nranks = g.nranks;
+    a.scalar = g.scalar;
+    for (int r = 0; r < g.nranks && r < kMaxRanks; r++)
+        a.peer_xf[r] = g.peer_xf[r];
+    a.my_xf = g.my_xf;
+    a.off = g.off;
+    a.timeout_ns = g.timeout_ns;
+    a.err = g.err;
+    k_norm_exchange<<<1, 32, 0, st>>>(a);
     COUNT_LAUNCH();
 }
 

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 
 #include "geom.h"
+#include "halo.cuh"
 #include "lu_band.cuh"
 
 namespace mgb {
@@ -27,17 +28,18 @@ void launch_set_dirichlet(const Geo &g, double *a, double h, cudaStream_t st);
 // one colour of the RB-GS smoother over local planes [il_lo, il_hi)
 // (mg_3d.h:432-443, 658-702)
 void launch_half_sweep(const Geo &g, double *v, const double *d, double hSq,
-                       int colour, int il_lo, int il_hi, cudaStream_t st);
+                       int colour, int il_lo, int il_hi, cudaStream_t st,
+                       const HaloCtl *h = nullptr);
 
 // the same when every neighbour is known to be zero (first sweep of a coarse level)
 void launch_first_sweep_zero(const Geo &g, double *v, const double *d, double hSq, int colour,
-                             int il_lo, int il_hi, cudaStream_t st);
+                             int il_lo, int il_hi, cudaStream_t st, const HaloCtl *h = nullptr);
 
 // residual (mg_3d.h:794-842) over local planes [il_lo, il_hi); r may be
 // nullptr; the sum of squares lands in *out_sumsq (device) via `partials`
 void launch_residual(const Geo &g, const double *v, const double *d, double *r,
                      double invHsq, int il_lo, int il_hi, double *partials,
-                     double *out_sumsq, cudaStream_t st);
+                     double *out_sumsq, cudaStream_t st, const HaloCtl *h = nullptr);
 
 // full-weighting restriction r(fine) -> d(coarse) (mg_3d.h:844-998) for local
 // coarse planes [Il_lo, Il_hi)
@@ -47,14 +49,15 @@ void launch_restrict(const Geo &gf, const double *rf, const Geo &gc, double *dc,
 // the two above in one pass, the fine residual never stored (17 B/DOF)
 void launch_residual_restrict(const Geo &gf, const double *vf, const double *df,
                               double invHsq, const Geo &gc, double *dc, int Il_lo,
-                              int Il_hi, cudaStream_t st);
+                              int Il_hi, cudaStream_t st, const HaloCtl *h = nullptr);
 
 // trilinear prolongation + correction (mg_3d.h:1000-1145) for local fine
 // planes [il_lo, il_hi)
 // cmask: bit c set = colour c is corrected (3 = the reference's operation; inside the
 // V-cycle only the colour the post-smoother does not overwrite first is needed)
 void launch_prolong_correct(const Geo &gc, const double *ec, const Geo &gf,
-                            double *ef, int il_lo, int il_hi, cudaStream_t st, int cmask = 3);
+                            double *ef, int il_lo, int il_hi, cudaStream_t st, int cmask = 3,
+                            const HaloCtl *h = nullptr);
 // a[p] = a[p] + 0. on the face points of colour `colour` in local planes [il_lo, il_hi):
 // what the reference's `ef[p] += 0.` does to a boundary value (-0. becomes +0.)
 void launch_add_zero_faces(const Geo &g, double *a, int colour, int il_lo, int il_hi,
@@ -81,34 +84,56 @@ void launch_finish_sum(const double *partials, int n, double *out, cudaStream_t 
 // (planes must then be ALL interior planes of the level, single-GPU levels only).
 bool tile_enabled();
 void tile_set(int on /* <0: keep */, long long min_plane /* <0: keep */);
+// h (partitioned levels): the fused halo waits / pushes of halo.cuh
 bool launch_tile_residual(const Geo &g, double *v, const double *d, double hSq, double invHsq,
                           int colour, int il_lo, int il_hi, double *partials, double *out_sumsq,
-                          cudaStream_t st);
+                          cudaStream_t st, const HaloCtl *h = nullptr);
 bool launch_tile_residual_restrict(const Geo &gf, double *vf, const double *df, double hSq,
                                    double invHsq, int colour, const Geo &gc, double *dc,
-                                   int Il_lo, int Il_hi, cudaStream_t st);
+                                   int Il_lo, int Il_hi, cudaStream_t st,
+                                   const HaloCtl *h = nullptr);
 
-// ---- halo exchange over NVLink peer memory (kernels.cu) ----
-// push: copy up to two contiguous runs of doubles into the neighbour GPU's
-// memory (IPC-mapped peer pointers), then -- once every block's stores are
-// fenced system-wide -- bump this direction's sequence number (*seq, local) and
-// release it into the neighbour's flag.  wait: spin (one thread) until the
-// local flag reaches the next expected sequence number (*expect, local).
-struct HaloRun {  // one direction: up to two contiguous runs (colours) + where to signal
-    const double *src[2] = {nullptr, nullptr};
-    double *dst[2] = {nullptr, nullptr};
-    long long n[2] = {0, 0};
+// ---- multi-GPU plumbing outside the compute kernels (kernels.cu; halo.cuh has the
+// fused part) ----
+// explicit halo step: copy up to four contiguous runs of doubles per direction into the
+// neighbour GPU's memory (IPC-mapped peer pointers), then -- once every block's stores are
+// fenced system-wide -- release this direction's sequence number into the neighbour's flag
+struct HaloRun {
+    const double *src[4] = {nullptr, nullptr, nullptr, nullptr};
+    double *dst[4] = {nullptr, nullptr, nullptr, nullptr};
+    long long n[4] = {0, 0, 0, 0};
     unsigned long long *peer_flag = nullptr;  // nullptr: nothing goes this way
-    unsigned long long *seq = nullptr;
-    unsigned int *done = nullptr;
+    unsigned int *count = nullptr;            // local arrival counter
+    unsigned long long off = 0;               // sequence offset within the epoch
 };
-// both directions in ONE launch, both waits in ONE launch
-void launch_halo_push(const HaloRun &up, const HaloRun &low, cudaStream_t st);
-// timeout_ns: give up after that long (0: never) and set bit 0 (lower neighbour) /
-// bit 1 (upper neighbour) of *err (host-mapped) instead of hanging or trapping
-void launch_halo_wait(const unsigned long long *flag0, unsigned long long *expect0,
-                      const unsigned long long *flag1, unsigned long long *expect1,
-                      unsigned long long timeout_ns, unsigned int *err, cudaStream_t st);
+void launch_halo_push(const HaloRun &up, const HaloRun &low, const unsigned long long *epoch,
+                      cudaStream_t st);
+// explicit wait for everything both neighbours were asked to send so far (h.wait_*)
+void launch_halo_wait(const HaloCtl &h, cudaStream_t st);
+// end of a collective operation (see halo.cuh)
+void launch_epoch_close(unsigned long long *xf, unsigned long long n_up, unsigned long long n_low,
+                        cudaStream_t st);
+// all-gather of the first replicated level's rhs slabs / sum of a scalar in rank order
+struct GatherHost {
+    int me, nranks;
+    const double *src[2];
+    long long n[2];
+    double *dst[kMaxRanks][2];
+    unsigned long long *peer_xf[kMaxRanks];
+    unsigned long long *my_xf;
+    unsigned long long off, timeout_ns;
+    unsigned int *err;
+};
+void launch_gather(const GatherHost &g, cudaStream_t st);
+struct NormHost {
+    int me, nranks;
+    double *scalar;
+    unsigned long long *peer_xf[kMaxRanks];
+    unsigned long long *my_xf;
+    unsigned long long off, timeout_ns;
+    unsigned int *err;
+};
+void launch_norm_exchange(const NormHost &g, cudaStream_t st);
 
 // ---- the deep coarse levels as one single-block kernel (tail.cu) ----
 struct TailLevel {
@@ -129,14 +154,14 @@ void launch_coarse_tail(const TailP &p, cudaStream_t st);
 
 // the half-sweep through the TMA ring (tile.cu); false: level too small, use the marching kernel
 bool launch_tile_half_sweep(const Geo &g, double *v, const double *d, double hSq, int colour,
-                            int il_lo, int il_hi, cudaStream_t st);
+                            int il_lo, int il_hi, cudaStream_t st, const HaloCtl *h = nullptr);
 
 // launch plan of a tile kernel (no launch): see tile.cu
 void tile_plan_query(int kind, const Geo &gf, const Geo *gc, int p_lo, int p_hi, long long *out);
 // prolongation + correction through the TMA ring (tile.cu); false: use launch_prolong_correct's
 // marching kernels
 bool launch_tile_prolong(const Geo &gc, const double *ec, const Geo &gf, double *ef, int il_lo,
-                         int il_hi, int cmask, cudaStream_t st);
+                         int il_hi, int cmask, cudaStream_t st, const HaloCtl *h = nullptr);
 
 // dense coarse operator + LU (mg_3d.h:147-273, gauss_elim.h:9-60)
 void launch_coarse_matrix(double *A, int ni, int nj, int nk, double h,

@@ -53,6 +53,7 @@
 #include <type_traits>
 
 #include "kernels.h"
+#include "halo.cuh"
 
 namespace mgb {
 
@@ -192,7 +193,19 @@ struct TileP {
     int p_lo, p_hi;    // NORM: fine local planes [p_lo,p_hi); RESTRICT: coarse local planes
     int chunk;         // planes per blockIdx.z
     int cmask;         // prolongation: bit c set = colour c is corrected (3: both)
+    HaloCtl h;         // partitioned level: fused halo waits / pushes (halo.cuh); epoch == nullptr: none
 };
+
+// Which chunk of planes a block works on.  On a partitioned level the chunks that hold
+// the slab's boundary planes go first (blockIdx.z = 0: the last chunk, 1: the first one),
+// so that their pushes into the neighbours' halos travel underneath the interior chunks.
+__device__ __forceinline__ int tile_chunk(const TileP &P)
+{
+    const int z = blockIdx.z, nz = gridDim.z;
+    if (!P.h.epoch || nz < 3)
+        return z;
+    return z == 0 ? nz - 1 : z - 1;
+}
 
 // SWEEP = -1: no fused sweep; 0/1: colour swept one plane ahead of the residual
 // MINB = resident blocks per SM the register budget is cut for: 1 -> 512
@@ -245,8 +258,9 @@ k_tile(const TileP P, const __grid_constant__ CUtensorMap tm_v,
     // ---- plane range of this chunk ----------------------------------------
     int ia, ib;            // residual planes [ia, ib) (fine, local)
     int Ia = 0, Ib = 0;    // RESTRICT: coarse planes of the chunk
+    const int zc = tile_chunk(P);
     if (RESTRICT) {
-        Ia = P.p_lo + blockIdx.z * P.chunk;
+        Ia = P.p_lo + zc * P.chunk;
         Ib = min(Ia + P.chunk, P.p_hi);
         const int Im0 = max(Ia, 1 - P.gc.i0);
         const int Im1 = min(Ib, P.gc.ni - 1 - P.gc.i0);
@@ -255,7 +269,7 @@ k_tile(const TileP P, const __grid_constant__ CUtensorMap tm_v,
         if (Im0 >= Im1)
             ib = ia;  // only boundary planes in this chunk
     } else {
-        ia = P.p_lo + blockIdx.z * P.chunk;
+        ia = P.p_lo + zc * P.chunk;
         ib = min(ia + P.chunk, P.p_hi);
     }
 
@@ -308,6 +322,11 @@ k_tile(const TileP P, const __grid_constant__ CUtensorMap tm_v,
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
+    // partitioned level: the chunks at the ends of the slab read halo planes
+    if (RESTRICT)
+        halo_wait_cta(P.h, Ia == P.p_lo, Ib == P.p_hi);
+    else
+        halo_wait_cta(P.h, ia == P.p_lo, ib == P.p_hi);
 
     // producer (thread 0): planes p with p - S <= dead may overwrite their slot
     int iss_p = pr0, iss_s = 0;
@@ -390,8 +409,12 @@ k_tile(const TileP P, const __grid_constant__ CUtensorMap tm_v,
                     const int ig = g.i0 + t;
                     const int Il = ((ig - 1) >> 1) - P.gc.i0;
                     const int cc = (P.gc.i0 + Il + cJ + cK) & 1;
+                    const double val = cint ? a : 0.;
                     P.dc[(long long)cc * P.gc.cs + ((long long)Il * P.gc.nj + cJ) * P.gc.kh +
-                         (cK >> 1)] = cint ? a : 0.;
+                         (cK >> 1)] = val;
+                    // my last coarse plane is the upper neighbour's coarse-rhs halo
+                    if (P.h.push_up.peer_flag && Il == P.h.push_up.plane[0])
+                        P.h.push_up.dst[cc][(long long)cJ * P.gc.kh + (cK >> 1)] = val;
                 }
                 cacc = sfresh;  // ... and opens I+1
                 have_cur = true;
@@ -648,8 +671,10 @@ k_tile(const TileP P, const __grid_constant__ CUtensorMap tm_v,
     if (!RESTRICT) {
         acc = tile_block_sum(acc);
         if (tid == 0)
-            P.partials[((size_t)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x] = acc;
+            P.partials[((size_t)zc * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x] = acc;
     }
+    if (RESTRICT && halo_takes_part(P.h.push_up, Ia, Ib))
+        halo_signal_cta(P.h, P.h.push_up);
 }
 
 // ---------------------------------------------------------------------------
@@ -681,7 +706,7 @@ k_tile_sweep(const TileP P, const __grid_constant__ CUtensorMap tm_v,
     const int j = jt0 + jl, mq = mq0 + ml;
     const bool calc = live && j >= 1 && j <= g.nj - 2 && mq >= 0 && mq < npair;
     const int kmax = g.nk - 2;
-    const int ia = P.p_lo + blockIdx.z * P.chunk;
+    const int ia = P.p_lo + tile_chunk(P) * P.chunk;
     const int ib = min(ia + P.chunk, P.p_hi);
     if (ia >= ib)
         return;
@@ -695,6 +720,10 @@ k_tile_sweep(const TileP P, const __grid_constant__ CUtensorMap tm_v,
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
+    halo_wait_cta(P.h, ia == P.p_lo, ib == P.p_hi);
+    // planes of this chunk whose new values also go into a neighbour's halo
+    const HaloPush &hu = P.h.push_up, &hl = P.h.push_low;
+    const bool pushes = P.h.epoch && (halo_takes_part(hu, ia, ib) || halo_takes_part(hl, ia, ib));
     int iss_p = pr0, iss_s = 0;
     auto issue_upto = [&](int dead) {
         if (tid != 0)
@@ -763,6 +792,8 @@ k_tile_sweep(const TileP P, const __grid_constant__ CUtensorMap tm_v,
                     pc[0] = r0;
                 else if (mk & 2)
                     pc[1] = r1;
+                if (pushes)  // boundary plane of the slab: the same store, into the peer's halo
+                    halo_mirror_pair(P.h, t, offq, mk & 1, mk & 2, r0, r1);
             }
             bot = mid;
             mid = top;
@@ -778,6 +809,12 @@ k_tile_sweep(const TileP P, const __grid_constant__ CUtensorMap tm_v,
         step(t, A, B);
         if (t + 1 < ib)
             step(t + 1, B, A);
+    }
+    if (pushes) {
+        if (halo_takes_part(hu, ia, ib))
+            halo_signal_cta(P.h, hu);
+        if (halo_takes_part(hl, ia, ib))
+            halo_signal_cta(P.h, hl);
     }
 }
 
@@ -877,7 +914,7 @@ k_tile_prolong(const TileP P, const double *__restrict__ ec,
     const int k0 = 4 * mq;
     const bool work = jl < TRt && j < g.nj && mq < npair && k0 < g.nk;
     const bool v1 = k0 + 1 < g.nk, v2 = k0 + 2 < g.nk, v3 = k0 + 3 < g.nk;
-    const int ia = P.p_lo + blockIdx.z * P.chunk;  // even global plane
+    const int ia = P.p_lo + tile_chunk(P) * P.chunk;  // even global plane
     const int ib = min(ia + P.chunk, P.p_hi);
     if (ia >= ib)
         return;
@@ -891,6 +928,7 @@ k_tile_prolong(const TileP P, const double *__restrict__ ec,
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
+    halo_wait_cta(P.h, ia == P.p_lo, ib == P.p_hi);  // the coarse rows read include halo planes
     int iss_p = pr0, iss_s = 0;
     auto issue_upto = [&](int dead) {
         if (tid != 0)
@@ -1018,7 +1056,7 @@ k_tile_prolong_one(const TileP P, const double *__restrict__ ec,
     const int o = mq >> 1;                      // its octet (mq0 is even)
     const int k0 = 4 * mq;
     const bool work = jl < TRt && j < g.nj && k0 < g.nk;
-    const int ia = P.p_lo + blockIdx.z * P.chunk;  // even global plane
+    const int ia = P.p_lo + tile_chunk(P) * P.chunk;  // even global plane
     const int ib = min(ia + P.chunk, P.p_hi);
     if (ia >= ib)
         return;
@@ -1032,6 +1070,7 @@ k_tile_prolong_one(const TileP P, const double *__restrict__ ec,
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
+    halo_wait_cta(P.h, ia == P.p_lo, ib == P.p_hi);  // the coarse rows read include halo planes
     int iss_p = pr0, iss_s = 0;
     auto issue_upto = [&](int dead) {
         if (tid != 0)
@@ -1412,7 +1451,7 @@ static bool tile_worthwhile(const Geo &g) { return (long long)g.nj * g.nk >= g_t
 // ALL interior planes of the level: values of planes outside are recomputed)
 bool launch_tile_residual(const Geo &g, double *v, const double *d, double hSq, double invHsq,
                           int colour, int il_lo, int il_hi, double *partials, double *out_sumsq,
-                          cudaStream_t st)
+                          cudaStream_t st, const HaloCtl *h)
 {
     if (!tile_enabled() || il_hi <= il_lo || !tile_worthwhile(g))
         return false;
@@ -1421,6 +1460,7 @@ bool launch_tile_residual(const Geo &g, double *v, const double *d, double hSq, 
         return false;
     c.p.v = v; c.p.vw = v; c.p.d = d; c.p.hSq = hSq; c.p.invHsq = invHsq;
     c.p.partials = partials; c.p.dc = nullptr;
+    c.p.h = h ? *h : HaloCtl{};
     const bool ok = colour < 0 ? launch_cfg<-1, false>(c, st)
                                : (colour == 0 ? launch_cfg<0, false>(c, st) : launch_cfg<1, false>(c, st));
     if (!ok)
@@ -1433,7 +1473,7 @@ bool launch_tile_residual(const Geo &g, double *v, const double *d, double hSq, 
 // with the half-sweep of `colour` fused in (single-GPU levels only)
 bool launch_tile_residual_restrict(const Geo &gf, double *vf, const double *df, double hSq,
                                    double invHsq, int colour, const Geo &gc, double *dc, int Il_lo,
-                                   int Il_hi, cudaStream_t st)
+                                   int Il_hi, cudaStream_t st, const HaloCtl *h)
 {
     if (!tile_enabled() || Il_hi <= Il_lo || !tile_worthwhile(gf))
         return false;
@@ -1442,13 +1482,18 @@ bool launch_tile_residual_restrict(const Geo &gf, double *vf, const double *df, 
         return false;
     c.p.v = vf; c.p.vw = vf; c.p.d = df; c.p.hSq = hSq; c.p.invHsq = invHsq;
     c.p.partials = nullptr; c.p.dc = dc;
+    c.p.h = h ? *h : HaloCtl{};
+    // the blocks whose chunk holds the coarse plane that goes to the upper neighbour
+    c.p.h.push_up.nblocks = halo_chunks_with(c.p.h.push_up, Il_lo, Il_hi, c.p.chunk) * c.grid.x * c.grid.y;
+    if (c.p.h.push_up.peer_flag && !c.p.h.push_up.nblocks)
+        return false;  // nobody would signal: the caller uses the plain kernel + an explicit step
     return colour < 0 ? launch_cfg<-1, true>(c, st)
                       : (colour == 0 ? launch_cfg<0, true>(c, st) : launch_cfg<1, true>(c, st));
 }
 
 // one colour of the smoother over local planes [il_lo, il_hi) through the TMA ring
 bool launch_tile_half_sweep(const Geo &g, double *v, const double *d, double hSq, int colour,
-                            int il_lo, int il_hi, cudaStream_t st)
+                            int il_lo, int il_hi, cudaStream_t st, const HaloCtl *h)
 {
     // measured (B200): 513^3 249 us vs 275 us for the L1-based marching kernel
     // (6.5 TB/s = 99 % of the measured copy peak), 1025^3 2.21 vs 2.24 ms, but
@@ -1465,6 +1510,9 @@ bool launch_tile_half_sweep(const Geo &g, double *v, const double *d, double hSq
     TileP &p = c.p;
     const size_t RS = p.TRt + 2, PW = 2 * (p.TQt + 2);
     p.v = v; p.vw = v; p.d = d; p.hSq = hSq; p.invHsq = 0.;
+    p.h = h ? *h : HaloCtl{};
+    p.h.push_up.nblocks = halo_chunks_with(p.h.push_up, il_lo, il_hi, p.chunk) * c.grid.x * c.grid.y;
+    p.h.push_low.nblocks = halo_chunks_with(p.h.push_low, il_lo, il_hi, p.chunk) * c.grid.x * c.grid.y;
     CUtensorMap tm_v, tm_d;
     if (!make_tensor_map(&tm_v, g, v, (int)PW, (int)RS, 1) ||
         !make_tensor_map(&tm_d, g, d, (int)PW, (int)RS, 1))
@@ -1491,7 +1539,7 @@ bool launch_tile_half_sweep(const Geo &g, double *v, const double *d, double hSq
 
 // prolongation + correction of local fine planes [il_lo, il_hi) through the TMA ring
 bool launch_tile_prolong(const Geo &gc, const double *ec, const Geo &gf, double *ef, int il_lo,
-                         int il_hi, int cmask, cudaStream_t st)
+                         int il_hi, int cmask, cudaStream_t st, const HaloCtl *h)
 {
     static const int on = env_int("MGB_TILE_PROLONG", 1);
     static const long long min_plane = env_int("MGB_TILE_PROLONG_MIN_PLANE", 200000);
@@ -1510,6 +1558,7 @@ bool launch_tile_prolong(const Geo &gc, const double *ec, const Geo &gf, double 
         p.gc = gc;
         p.cmask = cmask;
         p.v = ef; p.vw = ef; p.d = nullptr; p.hSq = 0.; p.invHsq = 0.;
+        p.h = h ? *h : HaloCtl{};
         CUtensorMap tm1;
         if (!make_tensor_map(&tm1, gf, ef, (int)PW, (int)RS, 1))
             return false;
@@ -1534,6 +1583,7 @@ bool launch_tile_prolong(const Geo &gc, const double *ec, const Geo &gf, double 
     p.cmask = cmask;
     const size_t RS = p.TRt + 2, PW = 2 * (p.TQt + 2);
     p.v = ef; p.vw = ef; p.d = nullptr; p.hSq = 0.; p.invHsq = 0.;
+    p.h = h ? *h : HaloCtl{};
     CUtensorMap tm_v;
     if (!make_tensor_map(&tm_v, gf, ef, (int)PW, (int)RS, cmask == 3 ? 2 : 1))
         return false;

@@ -50,7 +50,13 @@ class SlabMG:
     """mirror of mgb_create_dist + enqueue_cycle for one rank"""
 
     def __init__(self, lib, orc, coarse, levels, gs, rank, world, min_planes=2, min_points=0,
-                 shortcuts=False):
+                 shortcuts=False, fused=False):
+        # fused: the schedule of the P2P path (csrc/halo.cuh, api.cu) -- every half-sweep
+        # hands the swept COLOUR of its planes own_hi-2, own_hi-1 to the upper neighbour and
+        # of own_lo to the lower one (so no extra exchange precedes the restriction), the
+        # first unpartitioned level's right-hand side is all-gathered and the levels below
+        # are computed redundantly on every rank (no broadcast)
+        self.fused = fused
         # shortcuts: the two exact short-cuts libmgb's cycle takes -- coarse levels are
         # not zeroed (first RED half-sweep with the guess taken as 0), the
         # prolongation corrects RED points only (api.cu: enqueue_cycle, q_prolong)
@@ -98,7 +104,45 @@ class SlabMG:
             arr[lv.loc(plane)] = t.numpy()
 
     def works_on(self, q):
-        return q >= self.LD or self.rank == 0
+        return q >= self.LD or self.rank == 0 or self.fused
+
+    def _xchg_colour(self, lv, colour):
+        """fused schedule: the swept colour of the slab's boundary planes"""
+        has_low, has_up = self.rank > 0, self.rank < self.world - 1
+        ops, bufs = [], []
+        if has_up:
+            for pl in (lv.own_hi - 1, lv.own_hi - 2):
+                t = torch.from_numpy(lv.u[lv.loc(pl)].copy())
+                ops.append(dist.P2POp(dist.isend, t, self.rank + 1))
+        if has_low:
+            for pl in (lv.own_lo - 1, lv.own_lo - 2):
+                t = torch.empty((lv.nj, lv.nk), dtype=torch.float64)
+                bufs.append((t, pl))
+                ops.append(dist.P2POp(dist.irecv, t, self.rank - 1))
+            t = torch.from_numpy(lv.u[lv.loc(lv.own_lo)].copy())
+            ops.append(dist.P2POp(dist.isend, t, self.rank - 1))
+        if has_up:
+            t = torch.empty((lv.nj, lv.nk), dtype=torch.float64)
+            bufs.append((t, lv.own_hi))
+            ops.append(dist.P2POp(dist.irecv, t, self.rank + 1))
+        if ops:
+            for r in dist.batch_isend_irecv(ops):
+                r.wait()
+        for t, plane in bufs:
+            # only the INTERIOR points of the swept colour travel (the kernels mirror exactly
+            # the stores they make)
+            sel = self._colour_mask(lv, plane, plane + 1, colour)[0]
+            sel[0, :] = sel[-1, :] = False
+            sel[:, 0] = sel[:, -1] = False
+            lv.u[lv.loc(plane)][sel] = t.numpy()[sel]
+
+    def _after_sweep(self, lv, colour):
+        if not lv.dist:
+            return
+        if self.fused:
+            self._xchg_colour(lv, colour)
+        else:
+            self._xchg(lv.u, lv, lv.own_hi - 1, lv.own_lo - 1, lv.own_lo, lv.own_hi)
 
     # -- operators ---------------------------------------------------------
     def half_sweep(self, q, colour):
@@ -110,8 +154,7 @@ class SlabMG:
             a, b = lv.loc(lo - 1), lv.loc(hi + 1)
             # the oracle colours by LOCAL i: shift by the parity of the box origin
             self.orc.half_sweep(lv.u[a:b], lv.d[a:b], lv.h, colour ^ ((lo - 1) & 1))
-        if lv.dist:
-            self._xchg(lv.u, lv, lv.own_hi - 1, lv.own_lo - 1, lv.own_lo, lv.own_hi)
+        self._after_sweep(lv, colour)
 
     def _colour_mask(self, lv, lo, hi, colour):
         """points of global colour `colour` on local planes [lo, hi) (global indices)"""
@@ -134,8 +177,7 @@ class SlabMG:
             sel[:, 0, :] = sel[:, -1, :] = False
             sel[:, :, 0] = sel[:, :, -1] = False
             lv.u[lv.loc(lo):lv.loc(hi)][sel] = new[sel]
-        if lv.dist:
-            self._xchg(lv.u, lv, lv.own_hi - 1, lv.own_lo - 1, lv.own_lo, lv.own_hi)
+        self._after_sweep(lv, colour)
 
     def smooth(self, q, first_red, zero_guess=False):
         for it in range(self.gs):
@@ -164,7 +206,8 @@ class SlabMG:
             self.orc.residual(f.u, f.d, f.h, r)
             self.orc.restrict(r, c.d)
             return
-        self._xchg(f.u, f, f.own_hi - 2, f.own_lo - 2, None, None)  # deep halo
+        if not self.fused:
+            self._xchg(f.u, f, f.own_hi - 2, f.own_lo - 2, None, None)  # deep halo
         Ilo, Ihi = plan_slab(self.lib, c.ni, self.world, self.rank)
         Im0, Im1 = max(Ilo, 1), min(Ihi, c.ni - 1)  # interior coarse planes
         # fine box [2*Im0-2, 2*Im1]: its interior planes carry the residuals needed
@@ -179,6 +222,13 @@ class SlabMG:
                 c.d[c.loc(I)] = 0.0
         if c.dist:
             self._xchg(c.d, c, c.own_hi - 1, c.own_lo - 1, None, None)
+        elif self.fused:  # all-gather: every rank computes the levels below redundantly
+            for r in range(self.world):
+                lo, hi = plan_slab(self.lib, c.ni, self.world, r)
+                t = torch.from_numpy(c.d[lo:hi].copy()) if r == self.rank else \
+                    torch.empty((hi - lo, c.nj, c.nk), dtype=torch.float64)
+                dist.broadcast(t, r)
+                c.d[lo:hi] = t.numpy()
         else:  # gather on rank 0
             if self.rank > 0:
                 dist.send(torch.from_numpy(c.d[Ilo:Ihi].copy()), 0)
@@ -255,7 +305,7 @@ class SlabMG:
         self.smooth(q, True, zero_guess)
         self.residual_restrict(q)
         self.cycle_level(q - 1)
-        if q == self.LD:
+        if q == self.LD and not self.fused:
             t = torch.from_numpy(self.lv[q - 1].u)
             dist.broadcast(t, 0)
         self.prolong(q)

@@ -54,7 +54,8 @@ def test_slab_planner_tiles_and_nests(mgb):
     assert lib.mgb_plan_first_dist_level(3, 3, 3, 3, 8, 16, 0) == 3  # nothing splittable
 
 
-def _worker(rank, world, port, coarse, levels, gs, min_planes, cycles, q, shortcuts=False):
+def _worker(rank, world, port, coarse, levels, gs, min_planes, cycles, q, shortcuts=False,
+            fused=False):
     try:
         sys.path.insert(0, ROOT)
         sys.path.insert(0, HERE)
@@ -88,7 +89,7 @@ def _worker(rank, world, port, coarse, levels, gs, min_planes, cycles, q, shortc
             pass
         orc = Orc()
         slab = SlabMG(lib, orc, coarse, levels, gs, rank, world, min_planes=min_planes,
-                      shortcuts=shortcuts)
+                      shortcuts=shortcuts, fused=fused)
         serial = OrcMG(orc, coarse, levels, gs)
         top = levels - 1
         shape = serial.dims(top)
@@ -118,16 +119,20 @@ def _worker(rank, world, port, coarse, levels, gs, min_planes, cycles, q, shortc
         q.put((rank, "fail", traceback.format_exc()))
 
 
-@pytest.mark.parametrize("shortcuts", [False, True])
+@pytest.mark.parametrize("shortcuts,fused", [(False, False), (True, False), (True, True)])
 @pytest.mark.parametrize("coarse,levels,gs,min_planes", [
     ((3, 3, 3), 5, 2, 2),      # cube 33^3, partitioned down to level 1
-    ((3, 3, 3), 5, 2, 8),      # agglomeration: levels < 3 on rank 0
+    ((3, 3, 3), 5, 2, 8),      # levels < 3 unpartitioned (on rank 0 / replicated)
     ((5, 3, 3), 4, 1, 2),      # weak-scaling box (2P+1) x 3 x 3
 ])
-def test_partitioned_schedule_matches_serial_oracle(coarse, levels, gs, min_planes, shortcuts):
-    """shortcuts=True: the schedule as libmgb runs it now -- coarse levels never
-    zeroed (stale halos must all be refreshed by the exchanges before they are
-    read), RED-only prolongation without a halo fence -- over 3 cycles"""
+def test_partitioned_schedule_matches_serial_oracle(coarse, levels, gs, min_planes, shortcuts,
+                                                    fused):
+    """shortcuts=True: the schedule as libmgb runs it -- coarse levels never zeroed (stale
+    halos must all be refreshed by the exchanges before they are read), RED-only
+    prolongation without a halo fence -- over 3 cycles.  fused=True: the P2P path's
+    schedule (csrc/halo.cuh): only the swept colour of the boundary planes travels with
+    each half-sweep (two planes up, one down), no exchange in front of the restriction,
+    the unpartitioned levels all-gathered and computed redundantly on every rank."""
     import torch.multiprocessing as mp
     world = 2
     ctx = mp.get_context("spawn")
@@ -135,7 +140,7 @@ def test_partitioned_schedule_matches_serial_oracle(coarse, levels, gs, min_plan
     port = _free_port()
     procs = [ctx.Process(target=_worker,
                          args=(r, world, port, coarse, levels, gs, min_planes, 3 if shortcuts else 2,
-                               q, shortcuts))
+                               q, shortcuts, fused))
              for r in range(world)]
     for p in procs:
         p.start()
