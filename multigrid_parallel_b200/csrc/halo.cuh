@@ -55,7 +55,8 @@ enum {
     XF_DATA = 32,      // [rank]: "rank's slab of the gathered level has arrived here"
     XF_NORMFLAG = 48,  // [rank]: "rank's partial sum has arrived here"
     XF_NORMPART = 64,  // [2][kMaxRanks] doubles: partial sums by epoch parity
-    XF_SLOTS = 128
+    XF_GATHER_CNT = 128,  // [rank]: local arrival counters of the gather's copy blocks
+    XF_SLOTS = 160
 };
 
 struct HaloWait {

@@ -1326,10 +1326,10 @@ __global__ void k_epoch_close(unsigned long long *xf, unsigned long long n_up,
 
 // All-gather of the first replicated level's right-hand side: every rank has computed
 // its slab of coarse planes (two runs: one per colour) and needs everybody else's.
-// Block b talks to one peer: "I am done reading the old contents" -> wait for the same
-// from the peer -> copy my slab into the peer's array -> "your copy of my slab is
-// complete" -> wait for the peer's slab here.  Pushes come before waits on every rank,
-// so the pairwise handshakes cannot deadlock.
+// Three small kernels: "I am done reading the old contents" to every peer + wait for the
+// same from every peer; copy my slab into every peer's array (many blocks per peer, the
+// last one of a group tells the peer its copy is complete); wait for every peer's slab.
+// Signals come before waits on every rank, so the handshakes cannot deadlock.
 struct GatherArg {
     int me, nranks;
     const double *src[2];
@@ -1342,30 +1342,55 @@ struct GatherArg {
     unsigned int *err;
 };
 
-__global__ void __launch_bounds__(256) k_gather(const GatherArg a)
+// phase 0 (one block, thread p <-> peer p): "I am done reading the old contents" to every
+// peer, then wait for the same from every peer
+__global__ void k_gather_ready(const GatherArg a)
 {
-    int peer = blockIdx.x;
+    const int p = threadIdx.x;
+    if (p >= a.nranks || p == a.me)
+        return;
+    const unsigned long long v = a.my_xf[XF_EPOCH] * kHaloEpochStride + a.off;
+    halo_st_release(a.peer_xf[p] + XF_READY + a.me, v);
+    halo_spin(a.my_xf + XF_READY + p, v, a.timeout_ns, a.err, 4u);
+}
+
+// phase 1 (blockIdx.y <-> peer, gridDim.x blocks each): copy my slab into the peer's
+// array; the last block of a peer's group to finish tells the peer its copy is complete
+__global__ void __launch_bounds__(256) k_gather_copy(const GatherArg a)
+{
+    int peer = blockIdx.y;
     if (peer >= a.me)
         peer++;
-    const unsigned long long v = a.my_xf[XF_EPOCH] * kHaloEpochStride + a.off;
-    if (threadIdx.x == 0) {
-        halo_st_release(a.peer_xf[peer] + XF_READY + a.me, v);
-        halo_spin(a.my_xf + XF_READY + peer, v, a.timeout_ns, a.err, 4u);
-    }
-    __syncthreads();
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const long long t0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
 #pragma unroll
     for (int k = 0; k < 2; k++) {
         const double2 *s = reinterpret_cast<const double2 *>(a.src[k]);
         double2 *o = reinterpret_cast<double2 *>(a.dst[peer][k]);
-        for (long long t = threadIdx.x; 2 * t < a.n[k]; t += blockDim.x)
+        for (long long t = t0; 2 * t < a.n[k]; t += stride)
             o[t] = s[t];
     }
-    __threadfence_system();
     __syncthreads();
     if (threadIdx.x == 0) {
-        halo_st_release(a.peer_xf[peer] + XF_DATA + a.me, v);
-        halo_spin(a.my_xf + XF_DATA + peer, v, a.timeout_ns, a.err, 4u);
+        __threadfence_system();
+        unsigned int *cnt = reinterpret_cast<unsigned int *>(a.my_xf + XF_GATHER_CNT + peer);
+        if (atomicAdd(cnt, 1u) == gridDim.x - 1) {
+            *cnt = 0;
+            __threadfence_system();
+            halo_st_release(a.peer_xf[peer] + XF_DATA + a.me,
+                            a.my_xf[XF_EPOCH] * kHaloEpochStride + a.off);
+        }
     }
+}
+
+// phase 2 (one block, thread p <-> peer p): wait for every peer's slab
+__global__ void k_gather_wait(const GatherArg a)
+{
+    const int p = threadIdx.x;
+    if (p >= a.nranks || p == a.me)
+        return;
+    halo_spin(a.my_xf + XF_DATA + p, a.my_xf[XF_EPOCH] * kHaloEpochStride + a.off, a.timeout_ns,
+              a.err, 4u);
 }
 
 // Sum of one device scalar over the ranks, in RANK ORDER on every rank (bitwise the same
@@ -1468,8 +1493,16 @@ void launch_gather(const GatherHost &g, cudaStream_t st)
     a.off = g.off;
     a.timeout_ns = g.timeout_ns;
     a.err = g.err;
-    k_gather<<<g.nranks - 1, 256, 0, st>>>(a);
-    COUNT_LAUNCH();
+    long long most = a.n[0] > a.n[1] ? a.n[0] : a.n[1];
+    long long nb = (most / 2 + 256 * 4 - 1) / (256 * 4);  // ~4 x 16 B per thread and run
+    if (nb > 32)
+        nb = 32;
+    if (nb < 1)
+        nb = 1;
+    k_gather_ready<<<1, 32, 0, st>>>(a);
+    k_gather_copy<<<dim3((unsigned)nb, g.nranks - 1), 256, 0, st>>>(a);
+    k_gather_wait<<<1, 32, 0, st>>>(a);
+    g_launches += 3;
 }
 
 void launch_norm_exchange(const NormHost &g, cudaStream_t st)
