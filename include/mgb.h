@@ -130,6 +130,9 @@ int mgb_error_sumsq(mgb_solver *s, double *sumsq);
  *                  (mg_3d.h:1000-1145)
  * mgb_coarse_solve      : solveWithLU on level 0 (gauss_elim.h:31-60) */
 int mgb_half_sweep(mgb_solver *s, int level, int colour);
+/* tuning aid, not part of the reference's API: the same over the local planes
+ * [il_lo, il_hi) only (what one rank of a partitioned solver runs on its slab) */
+int mgb_debug_half_sweep_range(mgb_solver *s, int level, int colour, int il_lo, int il_hi);
 int mgb_smooth(mgb_solver *s, int level, int iters, int first_red);
 int mgb_residual(mgb_solver *s, int level, int store_r, double *sumsq);
 int mgb_restrict(mgb_solver *s, int level);

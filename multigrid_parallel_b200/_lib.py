@@ -71,6 +71,7 @@ def load_library():
     L.mgb_error_sumsq.argtypes = [vp, c_dp]
     L.mgb_half_sweep.argtypes = [vp, i, i]
     L.mgb_smooth.argtypes = [vp, i, i, i]
+    L.mgb_debug_half_sweep_range.argtypes = [vp, i, i, i, i]
     L.mgb_residual.argtypes = [vp, i, i, c_dp]
     L.mgb_restrict.argtypes = [vp, i]
     L.mgb_residual_restrict.argtypes = [vp, i]

@@ -1610,6 +1610,21 @@ extern "C" int mgb_half_sweep(mgb_solver *s, int level, int colour)
     return nccl_status();
 }
 
+// tuning aid (not part of the reference's API): one colour over the local planes
+// [il_lo, il_hi) only -- what a rank of a partitioned solver runs on its slab
+extern "C" int mgb_debug_half_sweep_range(mgb_solver *s, int level, int colour, int il_lo,
+                                          int il_hi)
+{
+    OP_PROLOGUE(level, 0);
+    Level &lv = s->lv[level];
+    if (lv.dist || il_lo < 1 || il_hi > lv.g.li - 1 || il_lo >= il_hi)
+        return fail("mgb_debug_half_sweep_range: bad range or partitioned level");
+    launch_half_sweep(lv.g, lv.a[MGB_U].base, lv.a[MGB_D].base, lv.hSq, colour ? 1 : 0, il_lo, il_hi,
+                      s->st);
+    CKLAUNCH();
+    return 0;
+}
+
 extern "C" int mgb_smooth(mgb_solver *s, int level, int iters, int first_red)
 {
     OP_PROLOGUE(level, 0);

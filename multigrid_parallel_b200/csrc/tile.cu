@@ -1185,7 +1185,9 @@ int tile_max_threads();
 // about 52 fine planes are best -- 341-plane chunks at 1025^3 cost 10-20 %,
 // 24-plane chunks at 513^3 2-4 % (each chunk re-reads 2-4 planes to start up) --
 // as long as the launch still has >= 4 blocks per resident slot; never fewer
-// than `minchunk` fine planes per chunk.  `unit` = fine planes per counted plane.
+// than `minchunk` fine planes per chunk (12: a 64-plane slab of 513^2 planes -- one rank's
+// share of that level of 1025^3 on 8 GPUs -- takes 38.6 us in 5 chunks, 49.1 us in the 2
+// chunks a minimum of 24 allows).  `unit` = fine planes per counted plane.
 int plan_chunks(int nplanes, int unit, long long per_layer, int minchunk)
 {
     static const int target = env_int("MGB_TILE_CHUNK", 52);
@@ -1261,7 +1263,7 @@ bool shape_cfg(TileCfg &c, const Geo &gf, bool sweep, bool restr, const Geo *gc,
 TileCfg make_cfg(const Geo &gf, bool sweep, bool restr, const Geo *gc, int p_lo, int p_hi)
 {
     TileCfg c{};
-    const int minchunk = env_int("MGB_TILE_MINCHUNK", 24);
+    const int minchunk = env_int("MGB_TILE_MINCHUNK", 12);
     const int q_env = env_int("MGB_TILE_Q", 0), r_env = env_int("MGB_TILE_R", 0);
     const int qcap = q_env > 0 ? q_env : (restr ? 33 : 43);
     if (r_env > 0) {
@@ -1393,7 +1395,7 @@ static bool plan_simple(TileCfg &c, const Geo &g, int il_lo, int il_hi, int rows
     c.grid.y = (g.nj + p.TRo - 1) / p.TRo;
     const int nplanes = il_hi - il_lo;
     const long long per_layer = (long long)c.grid.x * c.grid.y;
-    const int want = plan_chunks(nplanes, 1, per_layer, env_int("MGB_TILE_MINCHUNK", 24));
+    const int want = plan_chunks(nplanes, 1, per_layer, env_int("MGB_TILE_MINCHUNK", 12));
     p.chunk = (nplanes + want - 1) / want;
     if (pairs)
         p.chunk += p.chunk & 1;
