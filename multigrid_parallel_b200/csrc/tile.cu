@@ -466,14 +466,19 @@ k_tile(const TileP P, const __grid_constant__ CUtensorMap tm_v,
         int s = (g.i0 + ia + j) & 1;                 // row parity on plane t
         int offE = s ? col1 : 0, offO = col1 - offE;  // slot offsets of the E / O colour on plane t
         long long dE_off = s ? g.cs : 0;              // ... and in the rhs array
-        double2 botE = z2, midE = z2, botO = z2, midO = z2;
+        // the own column of planes t-1, t, t+1 lives in three register sets that ROTATE
+        // roles from step to step (the step loop is unrolled by six = lcm(2 rhs sets, 3
+        // plane sets)): copying bot <- mid <- top every plane cost 9 % of all issued
+        // instructions (IMAD.MOV, ncu source page)
+        struct Col { double2 E, O; };
+        Col R0{z2, z2}, R1{z2, z2}, R2{z2, z2};
         Pre A{z2, z2}, B{z2, z2};
         const double *q_cur = ring + slot_d + so;  // own pair, plane t, colour 0
         int n_s = 2;                                // slot of plane t+1
         if (live) {
             const double *sa = ring + so;  // plane ia-1: parities swapped
-            botE = ld2(sa + offO); botO = ld2(sa + offE);
-            midE = ld2(q_cur + offE); midO = ld2(q_cur + offO);
+            R0.E = ld2(sa + offO); R0.O = ld2(sa + offE);
+            R1.E = ld2(q_cur + offE); R1.O = ld2(q_cur + offO);
         }
         const double *pd = P.d + (long long)ia * g.pj + offq;  // rhs colour 0, plane t
         if (calc) {
@@ -481,7 +486,9 @@ k_tile(const TileP P, const __grid_constant__ CUtensorMap tm_v,
             A.dO = ld2(pd + (g.cs - dE_off));
         }
         const bool mE0 = fk & 1, mE1 = fk & 2, mO0 = fk & 4, mO1 = fk & 8;
-        auto step = [&](int t, const Pre &cur, Pre &nxt, auto prev_parity) {
+        auto step = [&](int t, const Pre &cur, Pre &nxt, auto prev_parity, const Col &bot,
+                        const Col &mid, Col &top) {
+            const double2 botE = bot.E, botO = bot.O, midE = mid.E, midO = mid.O;
             wait_next();  // plane t+1
             const double *q_nxt = ring + n_s * slot_d + so;
             double n0 = 0., n1 = 0., n2 = 0., n3 = 0.;
@@ -489,6 +496,8 @@ k_tile(const TileP P, const __grid_constant__ CUtensorMap tm_v,
             if (live) {
                 // on plane t+1 the parities swap colours
                 const double2 topE = ld2(q_nxt + offO), topO = ld2(q_nxt + offE);
+                top.E = topE;
+                top.O = topO;
                 if (calc) {
                     if (t + 1 < ib) {
                         nxt.dE = ld2(pd + (g.cs - dE_off));
@@ -508,8 +517,6 @@ k_tile(const TileP P, const __grid_constant__ CUtensorMap tm_v,
                     n2 = mE1 ? rE1 : 0.;
                     n3 = mO1 ? rO1 : 0.;
                 }
-                botE = midE; midE = topE;
-                botO = midO; midO = topO;
                 put_residuals(n0, n1, n2, n3, true);
             }
             // the restriction of plane t-1 rides in the same barrier interval as the
@@ -525,20 +532,18 @@ k_tile(const TileP P, const __grid_constant__ CUtensorMap tm_v,
             __syncthreads();
             issue_upto(t);
         };
-        if (RESTRICT) {  // chunks start on an odd global plane: t - 1 is even in the first step
-            for (int t = ia; t < ib; t += 2) {
-                step(t, A, B, EvenT{});
-                if (t + 1 < ib)
-                    step(t + 1, B, A, OddT{});
-            }
-            accumulate(ib - 1, xoff ^ (4 * pl));
-        } else {
-            for (int t = ia; t < ib; t += 2) {
-                step(t, A, B, EvenT{});
-                if (t + 1 < ib)
-                    step(t + 1, B, A, OddT{});
-            }
+        // (RESTRICT: chunks start on an odd global plane, so t - 1 is even in the first step;
+        // the parity tag only matters there)
+        for (int t = ia; t < ib; t += 6) {
+            step(t, A, B, EvenT{}, R0, R1, R2);
+            if (t + 1 < ib) step(t + 1, B, A, OddT{}, R1, R2, R0);
+            if (t + 2 < ib) step(t + 2, A, B, EvenT{}, R2, R0, R1);
+            if (t + 3 < ib) step(t + 3, B, A, OddT{}, R0, R1, R2);
+            if (t + 4 < ib) step(t + 4, A, B, EvenT{}, R1, R2, R0);
+            if (t + 5 < ib) step(t + 5, B, A, OddT{}, R2, R0, R1);
         }
+        if (RESTRICT)
+            accumulate(ib - 1, xoff ^ (4 * pl));
     } else {
         // =====================================================================
         // fused: colour c = SWEEP is relaxed on plane t+1, then the residual of
@@ -1035,6 +1040,19 @@ __device__ __forceinline__ TC5 t_ld_c5(const Geo &gc, const double *__restrict__
     return r;
 }
 
+// the coarse rows a thread will read for coarse plane Il, pulled towards the SM ahead of
+// time: the loads themselves (t_ld_c5) are issued only one fine plane before their use,
+// and an L2 / DRAM round trip is longer than that step (ncu: long-scoreboard stalls 5.2 of
+// 11 warp-cycles per issue in round 2's first capture)
+__device__ __forceinline__ void t_prefetch_c5(const Geo &gc, const double *__restrict__ ec, int Il,
+                                              int J, int o)
+{
+    const int S = (gc.i0 + Il + J) & 1;
+    const long long row = ((long long)Il * gc.nj + J) * gc.kh + 2 * o;
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(ec + (long long)S * gc.cs + row));
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(ec + (long long)(S ^ 1) * gc.cs + row));
+}
+
 template <int COLOUR>
 __global__ void __launch_bounds__(384, 2)
 k_tile_prolong_one(const TileP P, const double *__restrict__ ec,
@@ -1148,6 +1166,11 @@ k_tile_prolong_one(const TileP P, const double *__restrict__ ec,
         if (work && has_odd) {  // coarse plane I+1: requested now, used by the odd plane
             B0 = t_ld_c5(gc, ec, I + 1, J0, o);
             B1 = oj ? t_ld_c5(gc, ec, I + 1, J0 + 1, o) : B0;
+            if (t + 3 < ib) {  // ... and plane I+2 starts its way up for the next pair
+                t_prefetch_c5(gc, ec, I + 2, J0, o);
+                if (oj)
+                    t_prefetch_c5(gc, ec, I + 2, J0 + 1, o);
+            }
         }
         plane(t, 0);
         if (has_odd) {
