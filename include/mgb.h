@@ -163,6 +163,10 @@ int mgb_coarse_info(const mgb_solver *s, int *n, int *half_bandwidth, double *fa
  * mgb_solve = the driver loop test_mg_3d.c:40-66: cycle while
  * sqrt(sumsq) > threshold; history[c] = norm after cycle c+1. */
 int mgb_vcycle(mgb_solver *s, double *sumsq);
+/* n cycles enqueued back to back; only the last norm is read back (no per-cycle host
+ * round trip: for a fixed cycle count, where the driver loop test_mg_3d.c:40-66 would
+ * not look at the intermediate norms anyway) */
+int mgb_vcycles(mgb_solver *s, int n, double *sumsq);
 /* mgb_fmg_init = SolverFMGInitialize (mg_3d.h:1364-1404; upstream keeps it
  * commented out, the live copy mg_dirichlet_analytic.c:771-806 predates today's
  * vcycle signature): coarsest LU solve, then per level interpolate the coarser

@@ -82,6 +82,7 @@ def load_library():
     L.mgb_coarse_lu_download.argtypes = [vp, C.c_void_p]
     L.mgb_coarse_info.argtypes = [vp, c_ip, c_ip, c_dp]
     L.mgb_vcycle.argtypes = [vp, c_dp]
+    L.mgb_vcycles.argtypes = [vp, i, c_dp]
     L.mgb_fmg_init.argtypes = [vp, c_dp]
     L.mgb_solve.argtypes = [vp, d, i, c_dp, c_ip]
     L.mgb_timing.argtypes = [vp, i, i, c_ip, c_dp]

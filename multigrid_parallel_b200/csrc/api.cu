@@ -1900,7 +1900,8 @@ static void bump_calls_like_cycle(mgb_solver *s)
     s->calls[MGB_ST_RECURSE]++;
 }
 
-extern "C" int mgb_vcycle(mgb_solver *s, double *sumsq)
+// one cycle on the stream; `fetch`: read the norm back (synchronises)
+static int vcycle_impl(mgb_solver *s, double *sumsq, bool fetch)
 {
     if (bind(s))
         return 1;
@@ -1964,11 +1965,28 @@ extern "C" int mgb_vcycle(mgb_solver *s, double *sumsq)
             return 1;
     }
     bump_calls_like_cycle(s);
+    if (!fetch)
+        return 0;
     double v;
     if (fetch_scalar(s, 0, &v))
         return 1;
     if (sumsq)
         *sumsq = v;
+    return 0;
+}
+
+extern "C" int mgb_vcycle(mgb_solver *s, double *sumsq) { return vcycle_impl(s, sumsq, true); }
+
+// n cycles back to back on the stream, the host reads only the last norm: a fixed number
+// of cycles (a preconditioner application, or timing the device alone) does not pay the
+// per-cycle round trip of the reference's `while (norm > cmpNorm)` loop
+extern "C" int mgb_vcycles(mgb_solver *s, int n, double *sumsq)
+{
+    if (n < 1)
+        return fail("mgb_vcycles: n >= 1");
+    for (int c = 0; c < n; c++)
+        if (vcycle_impl(s, sumsq, c == n - 1 || s->opt_profile))
+            return 1;
     return 0;
 }
 

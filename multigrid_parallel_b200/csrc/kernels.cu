@@ -11,6 +11,7 @@
 #include <cstdlib>
 
 #include "kernels.h"
+#include "launch.h"
 #include "devmath.cuh"
 
 namespace mgb {
@@ -67,6 +68,7 @@ __device__ __forceinline__ double block_sum(double x)
 __global__ void __launch_bounds__(1024) k_finish_sum(const double *partials, int n,
                                                      double *out)
 {
+    pdl_enter();
     double acc = 0.;
     for (int t = threadIdx.x; t < n; t += blockDim.x)
         acc = __dadd_rn(acc, partials[t]);
@@ -164,7 +166,7 @@ void launch_unpack_range(const Geo &g, const double *split, double *nat, long lo
 
 void launch_finish_sum(const double *partials, int n, double *out, cudaStream_t st)
 {
-    k_finish_sum<<<1, 1024, 0, st>>>(partials, n, out);
+    launch_k(k_finish_sum, 1, 1024, 0, st, partials, n, out);
     COUNT_LAUNCH();
 }
 
@@ -297,6 +299,7 @@ k_half_sweep(Geo g, const double *__restrict__ vo, double *__restrict__ vc,
              const double *__restrict__ dc, double hSq, int il_lo, int il_hi,
              int chunk)
 {
+    pdl_enter();
     const int npair = g.kh >> 1;
     const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= (g.pj >> 1))
@@ -361,6 +364,7 @@ k_half_sweep_pipe(Geo g, const double *__restrict__ vo, double *__restrict__ vc,
                   const double *__restrict__ dc, double hSq, int il_lo, int il_hi, int chunk,
                   const HaloCtl h)
 {
+    pdl_enter();
     const int npair = g.kh >> 1;
     const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const int ia = il_lo + blockIdx.y * chunk;
@@ -450,6 +454,7 @@ __global__ void __launch_bounds__(256)
 k_first_sweep_zero(Geo g, double *__restrict__ vc, const double *__restrict__ dc, double hSq,
                    int il_lo, int il_hi, const HaloCtl h)
 {
+    pdl_enter();
     const int npair = g.kh >> 1;
     const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const int il = il_lo + blockIdx.y;
@@ -494,9 +499,9 @@ void launch_first_sweep_zero(const Geo &g, double *v, const double *d, double hS
     h.push_up.nblocks = halo_chunks_with(h.push_up, il_lo, il_hi, 1) * grid.x;
     h.push_low.nblocks = halo_chunks_with(h.push_low, il_lo, il_hi, 1) * grid.x;
     if (colour)
-        k_first_sweep_zero<1><<<grid, 256, 0, st>>>(g, v + g.cs, d + g.cs, hSq, il_lo, il_hi, h);
+        launch_k(k_first_sweep_zero<1>, grid, 256, 0, st, g, v + g.cs, d + g.cs, hSq, il_lo, il_hi, h);
     else
-        k_first_sweep_zero<0><<<grid, 256, 0, st>>>(g, v, d, hSq, il_lo, il_hi, h);
+        launch_k(k_first_sweep_zero<0>, grid, 256, 0, st, g, v, d, hSq, il_lo, il_hi, h);
     COUNT_LAUNCH();
 }
 
@@ -517,17 +522,17 @@ void launch_half_sweep(const Geo &g, double *v, const double *d, double hSq,
         h.push_low.nblocks = halo_chunks_with(h.push_low, il_lo, il_hi, c.chunk) * c.grid.x;
         if (hp) {
             if (colour)
-                k_half_sweep_pipe<1, true><<<c.grid, c.block, 0, st>>>(g, v, v + g.cs, d + g.cs, hSq,
+                launch_k(k_half_sweep_pipe<1, true>, c.grid, c.block, 0, st, g, v, v + g.cs, d + g.cs, hSq,
                                                                        il_lo, il_hi, c.chunk, h);
             else
-                k_half_sweep_pipe<0, true><<<c.grid, c.block, 0, st>>>(g, v + g.cs, v, d, hSq, il_lo,
+                launch_k(k_half_sweep_pipe<0, true>, c.grid, c.block, 0, st, g, v + g.cs, v, d, hSq, il_lo,
                                                                        il_hi, c.chunk, h);
         } else {
             if (colour)
-                k_half_sweep_pipe<1, false><<<c.grid, c.block, 0, st>>>(g, v, v + g.cs, d + g.cs, hSq,
+                launch_k(k_half_sweep_pipe<1, false>, c.grid, c.block, 0, st, g, v, v + g.cs, d + g.cs, hSq,
                                                                         il_lo, il_hi, c.chunk, h);
             else
-                k_half_sweep_pipe<0, false><<<c.grid, c.block, 0, st>>>(g, v + g.cs, v, d, hSq, il_lo,
+                launch_k(k_half_sweep_pipe<0, false>, c.grid, c.block, 0, st, g, v + g.cs, v, d, hSq, il_lo,
                                                                         il_hi, c.chunk, h);
         }
         COUNT_LAUNCH();
@@ -536,10 +541,10 @@ void launch_half_sweep(const Geo &g, double *v, const double *d, double hSq,
     static const int occ = resident_blocks(k_half_sweep<1>, 256, 0);
     const MarchCfg c = march_cfg(g, il_hi - il_lo, 256, occ);
     if (colour)
-        k_half_sweep<1><<<c.grid, c.block, 0, st>>>(g, v, v + g.cs, d + g.cs, hSq,
+        launch_k(k_half_sweep<1>, c.grid, c.block, 0, st, g, v, v + g.cs, d + g.cs, hSq,
                                                     il_lo, il_hi, c.chunk);
     else
-        k_half_sweep<0><<<c.grid, c.block, 0, st>>>(g, v + g.cs, v, d, hSq, il_lo,
+        launch_k(k_half_sweep<0>, c.grid, c.block, 0, st, g, v + g.cs, v, d, hSq, il_lo,
                                                     il_hi, c.chunk);
     COUNT_LAUNCH();
 }
@@ -554,6 +559,7 @@ k_residual(Geo g, const double *__restrict__ v, const double *__restrict__ d,
            double *__restrict__ r, double invHsq, int il_lo, int il_hi, int chunk,
            double *__restrict__ partials, const HaloCtl h)
 {
+    pdl_enter();
     const int npair = g.kh >> 1;
     const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     double acc = 0.;
@@ -634,13 +640,13 @@ void launch_residual(const Geo &g, const double *v, const double *d, double *r,
         c.grid.y = (il_hi - il_lo + c.chunk - 1) / c.chunk;
     }
     if (r)
-        k_residual<true><<<c.grid, c.block, 0, st>>>(g, v, d, r, invHsq, il_lo, il_hi,
+        launch_k(k_residual<true>, c.grid, c.block, 0, st, g, v, d, r, invHsq, il_lo, il_hi,
                                                      c.chunk, partials, h);
     else
-        k_residual<false><<<c.grid, c.block, 0, st>>>(g, v, d, nullptr, invHsq, il_lo,
+        launch_k(k_residual<false>, c.grid, c.block, 0, st, g, v, d, nullptr, invHsq, il_lo,
                                                       il_hi, c.chunk, partials, h);
     COUNT_LAUNCH();
-    k_finish_sum<<<1, 1024, 0, st>>>(partials, (int)(c.grid.x * c.grid.y), out_sumsq);
+    launch_k(k_finish_sum, 1, 1024, 0, st, partials, (int)(c.grid.x * c.grid.y), out_sumsq);
     COUNT_LAUNCH();
 }
 
@@ -651,6 +657,7 @@ __global__ void __launch_bounds__(256)
 k_restrict(Geo gf, const double *__restrict__ rf, Geo gc, double *__restrict__ dc,
            int Il_lo, int Il_hi)
 {
+    pdl_enter();
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long per_colour = (long long)(Il_hi - Il_lo) * gc.pj;
     if (t >= 2 * per_colour)
@@ -693,7 +700,7 @@ void launch_restrict(const Geo &gf, const double *rf, const Geo &gc, double *dc,
     if (Il_hi <= Il_lo)
         return;
     const long long total = 2LL * (Il_hi - Il_lo) * gc.pj;
-    k_restrict<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(gf, rf, gc, dc, Il_lo,
+    launch_k(k_restrict, (unsigned)((total + 255) / 256), 256, 0, st, gf, rf, gc, dc, Il_lo,
                                                                Il_hi);
     COUNT_LAUNCH();
 }
@@ -723,6 +730,7 @@ k_residual_restrict(Geo gf, const double *__restrict__ v, const double *__restri
                     double invHsq, Geo gc, double *__restrict__ dc, int Il_lo, int Il_hi,
                     int chunk, int TY, const HaloCtl h)
 {
+    pdl_enter();
     extern __shared__ double rs_all[];
     const int npair = gf.kh >> 1;
     const int R = 2 * TY + 1;
@@ -905,7 +913,7 @@ void launch_residual_restrict(const Geo &gf, const double *vf, const double *df,
     const unsigned by = (nplanes + chunk - 1) / chunk;
     HaloCtl h = hp ? *hp : HaloCtl{};
     h.push_up.nblocks = halo_chunks_with(h.push_up, Il_lo, Il_hi, chunk) * bx;
-    k_residual_restrict<1024><<<dim3(bx, by), threads, sh, st>>>(gf, vf, df, invHsq, gc, dc,
+    launch_k(k_residual_restrict<1024>, dim3(bx, by), threads, sh, st, gf, vf, df, invHsq, gc, dc,
                                                                Il_lo, Il_hi, chunk, TY, h);
     COUNT_LAUNCH();
 }
@@ -943,6 +951,7 @@ __global__ void __launch_bounds__(256)
 k_prolong_correct(Geo gc, const double *__restrict__ ec, Geo gf,
                   double *__restrict__ ef, int il_lo, int il_hi, int chunk)
 {
+    pdl_enter();
     const int npair = gf.kh >> 1;
     const long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= (gf.pj >> 1))
@@ -1041,6 +1050,7 @@ __global__ void __launch_bounds__(256, 2)
 k_prolong_correct8(Geo gc, const double *__restrict__ ec, Geo gf, double *ef, int il_lo,
                    int il_hi, int chunk, int cmask, const HaloCtl h)
 {
+    pdl_enter();
     const int noct = gf.kh >> 2;
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const int ia = il_lo + blockIdx.y * chunk;
@@ -1158,6 +1168,7 @@ k_prolong_correct8(Geo gc, const double *__restrict__ ec, Geo gf, double *ef, in
 __global__ void __launch_bounds__(256)
 k_add_zero_faces(Geo g, double *__restrict__ a, int colour, int il_lo, int il_hi)
 {
+    pdl_enter();
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     double *base = a + (long long)colour * g.cs;
     const int lo_face = -g.i0, hi_face = g.ni - 1 - g.i0;  // local indices of the i-faces
@@ -1215,7 +1226,7 @@ void launch_add_zero_faces(const Geo &g, double *a, int colour, int il_lo, int i
     const long long n0 = 2 * g.pj, n1 = (long long)(il_hi - il_lo) * 2 * g.kh,
                     n2 = (long long)(il_hi - il_lo) * g.nj;
     const long long most = n0 > n1 ? (n0 > n2 ? n0 : n2) : (n1 > n2 ? n1 : n2);
-    k_add_zero_faces<<<dim3((unsigned)((most + 255) / 256), 3), 256, 0, st>>>(g, a, colour, il_lo,
+    launch_k(k_add_zero_faces, dim3((unsigned)((most + 255) / 256), 3), 256, 0, st, g, a, colour, il_lo,
                                                                             il_hi);
     COUNT_LAUNCH();
 }
@@ -1244,14 +1255,14 @@ void launch_prolong_correct(const Geo &gc, const double *ec, const Geo &gf,
         int chunk = (nplanes + nch - 1) / nch;
         chunk += chunk & 1;  // whole (even, odd) pairs per chunk
         const unsigned by = (unsigned)((nplanes + chunk - 1) / chunk);
-        k_prolong_correct8<<<dim3(bx, by), 256, 0, st>>>(gc, ec, gf, ef, il_lo, il_hi, chunk,
+        launch_k(k_prolong_correct8, dim3(bx, by), 256, 0, st, gc, ec, gf, ef, il_lo, il_hi, chunk,
                                                          cmask, hp ? *hp : HaloCtl{});
         COUNT_LAUNCH();
         return;
     }
     static const int occ = resident_blocks(k_prolong_correct, 256, 0);
     const MarchCfg c = march_cfg(gf, il_hi - il_lo, 256, occ);
-    k_prolong_correct<<<c.grid, c.block, 0, st>>>(gc, ec, gf, ef, il_lo, il_hi, c.chunk);
+    launch_k(k_prolong_correct, c.grid, c.block, 0, st, gc, ec, gf, ef, il_lo, il_hi, c.chunk);
     COUNT_LAUNCH();
 }
 
@@ -1274,6 +1285,7 @@ struct HaloDir {  // one direction of an explicit halo step: up to four runs + t
 __global__ void __launch_bounds__(256)
 k_halo_push(HaloDir up, HaloDir low, const unsigned long long *epoch)
 {
+    pdl_enter();
     // the first gridDim.x/2 blocks (or all, if only one direction is active)
     // serve `up`, the rest `low`
     const bool both = up.peer_flag && low.peer_flag;
@@ -1307,6 +1319,7 @@ k_halo_push(HaloDir up, HaloDir low, const unsigned long long *epoch)
 // thread 0 waits for the lower side, thread 1 for the upper one
 __global__ void k_halo_wait(HaloCtl h)
 {
+    pdl_enter();
     if (threadIdx.x == 0)
         halo_wait_one(h, h.wait_low, 1u);
     else if (threadIdx.x == 1)
@@ -1318,6 +1331,7 @@ __global__ void k_halo_wait(HaloCtl h)
 __global__ void k_epoch_close(unsigned long long *xf, unsigned long long n_up,
                               unsigned long long n_low)
 {
+    pdl_enter();
     const unsigned long long e = xf[XF_EPOCH];
     if (n_up)
         xf[XF_PREV_UP] = e * kHaloEpochStride + n_up;
@@ -1348,6 +1362,7 @@ struct GatherArg {
 // peer, then wait for the same from every peer
 __global__ void k_gather_ready(const GatherArg a)
 {
+    pdl_enter();
     const int p = threadIdx.x;
     if (p >= a.nranks || p == a.me)
         return;
@@ -1360,6 +1375,7 @@ __global__ void k_gather_ready(const GatherArg a)
 // array; the last block of a peer's group to finish tells the peer its copy is complete
 __global__ void __launch_bounds__(256) k_gather_copy(const GatherArg a)
 {
+    pdl_enter();
     int peer = blockIdx.y;
     if (peer >= a.me)
         peer++;
@@ -1388,6 +1404,7 @@ __global__ void __launch_bounds__(256) k_gather_copy(const GatherArg a)
 // phase 2 (one block, thread p <-> peer p): wait for every peer's slab
 __global__ void k_gather_wait(const GatherArg a)
 {
+    pdl_enter();
     const int p = threadIdx.x;
     if (p >= a.nranks || p == a.me)
         return;
@@ -1409,6 +1426,7 @@ struct NormArg {
 
 __global__ void k_norm_exchange(const NormArg a)
 {
+    pdl_enter();
     const int p = threadIdx.x;
     const unsigned long long e = a.my_xf[XF_EPOCH];
     const unsigned long long v = e * kHaloEpochStride + a.off;
@@ -1458,7 +1476,7 @@ void launch_halo_push(const HaloRun &up, const HaloRun &low, const unsigned long
         nb = 1;
     if (up.peer_flag && low.peer_flag)
         nb *= 2;
-    k_halo_push<<<(unsigned)nb, 256, 0, st>>>(a, b, epoch);
+    launch_k(k_halo_push, (unsigned)nb, 256, 0, st, a, b, epoch);
     COUNT_LAUNCH();
 }
 
@@ -1466,14 +1484,14 @@ void launch_halo_wait(const HaloCtl &h, cudaStream_t st)
 {
     if (!h.epoch || (!h.wait_low.flag && !h.wait_up.flag))
         return;
-    k_halo_wait<<<1, 2, 0, st>>>(h);
+    launch_k(k_halo_wait, 1, 2, 0, st, h);
     COUNT_LAUNCH();
 }
 
 void launch_epoch_close(unsigned long long *xf, unsigned long long n_up, unsigned long long n_low,
                         cudaStream_t st)
 {
-    k_epoch_close<<<1, 1, 0, st>>>(xf, n_up, n_low);
+    launch_k(k_epoch_close, 1, 1, 0, st, xf, n_up, n_low);
     COUNT_LAUNCH();
 }
 
@@ -1501,9 +1519,9 @@ void launch_gather(const GatherHost &g, cudaStream_t st)
         nb = 32;
     if (nb < 1)
         nb = 1;
-    k_gather_ready<<<1, 32, 0, st>>>(a);
-    k_gather_copy<<<dim3((unsigned)nb, g.nranks - 1), 256, 0, st>>>(a);
-    k_gather_wait<<<1, 32, 0, st>>>(a);
+    launch_k(k_gather_ready, 1, 32, 0, st, a);
+    launch_k(k_gather_copy, dim3((unsigned)nb, g.nranks - 1), 256, 0, st, a);
+    launch_k(k_gather_wait, 1, 32, 0, st, a);
     g_launches += 3;
 }
 
@@ -1519,7 +1537,7 @@ void launch_norm_exchange(const NormHost &g, cudaStream_t st)
     a.off = g.off;
     a.timeout_ns = g.timeout_ns;
     a.err = g.err;
-    k_norm_exchange<<<1, 32, 0, st>>>(a);
+    launch_k(k_norm_exchange, 1, 32, 0, st, a);
     COUNT_LAUNCH();
 }
 
@@ -1617,7 +1635,7 @@ void launch_sumsq(const double *a0, long long n0, const double *a1, long long n1
         COUNT_LAUNCH();
         total += (int)nb;
     }
-    k_finish_sum<<<1, 1024, 0, st>>>(partials, total, out);
+    launch_k(k_finish_sum, 1, 1024, 0, st, partials, total, out);
     COUNT_LAUNCH();
 }
 
@@ -1663,7 +1681,7 @@ void launch_error_sumsq(const Geo &g, const double *u, double h, int il_lo, int 
         nb = 1;
     k_error_sumsq<<<(unsigned)nb, 256, 0, st>>>(g, u, h, il_lo, il_hi, partials);
     COUNT_LAUNCH();
-    k_finish_sum<<<1, 1024, 0, st>>>(partials, (int)nb, out);
+    launch_k(k_finish_sum, 1, 1024, 0, st, partials, (int)nb, out);
     COUNT_LAUNCH();
 }
 

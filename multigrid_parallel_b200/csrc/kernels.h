@@ -135,7 +135,7 @@ struct NormHost {
 };
 void launch_norm_exchange(const NormHost &g, cudaStream_t st);
 
-// ---- the deep coarse levels as one single-block kernel (tail.cu) ----
+// ---- the deep coarse levels as one single-block, shared-memory kernel (tail.cu) ----
 struct TailLevel {
     Geo g;
     double *u, *d, *r;
@@ -146,8 +146,9 @@ struct TailP {
     int gs;           // smoothing iterations per leg
     int zero_top;     // level `top` starts from a zero guess (it is a coarse level)
     LuBand lu;        // factorised operator of level 0 (tile form)
-    int phase;        // 0: whole sub-cycle in one kernel is not possible any more (the LU
-                      // solve is its own kernel: register budget); 1: down leg, 2: up leg
+    int phase;        // 0: whole sub-cycle in one kernel (coarse system of <= 32 unknowns);
+                      // 1: down leg, 2: up leg, the stand-alone LU solve launched in between
+    int smem;         // working set held in shared memory (set by launch_coarse_tail)
     TailLevel lv[8];
 };
 void launch_coarse_tail(const TailP &p, cudaStream_t st);

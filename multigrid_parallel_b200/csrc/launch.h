@@ -1,0 +1,61 @@
+// launch.h -- every kernel of the cycle is launched through launch_k(): a plain launch
+// plus the "programmatic stream serialization" attribute (programmatic dependent launch).
+//
+// A V-cycle is ~60 dependent kernels, two thirds of them a few microseconds long; inside a
+// CUDA graph each kernel -> kernel edge still costs the drain of the previous grid, the
+// launch of the next one and its ramp-up.  With the attribute set, the blocks of kernel
+// N+1 may become resident while the last blocks of kernel N are still running; they sit in
+// `griddepcontrol.wait` (pdl_enter() below -- the first statement of every kernel
+// launched this way, executed by every thread before it touches memory) until kernel N has
+// completed and its writes are visible, so the data dependences between stages are exactly
+// those of a plain stream.  Transitively safe: kernel N cannot complete before its own
+// threads return from their wait, i.e. before kernel N-1 has completed.
+// The attribute survives stream capture (programmatic edges in the graph).
+// Measured on B200 (round 2, tools/cycle_case.py --batch 1, 513^3 ... 9^3 hierarchies): no
+// difference beyond run-to-run noise (3.695 vs 3.678 ms at 513^3, 0.212 vs 0.214 ms at
+// 129^3) -- the small kernels are bound by their own first-load latency and drain, which a
+// wait at the top cannot overlap -- so it is OFF by default; MGB_PDL=1 turns it on
+// (pdl_enter() is a no-op in hardware for a plain launch).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdlib>
+#include <utility>
+
+namespace mgb {
+
+inline bool pdl_enabled()
+{
+    static const bool on = getenv("MGB_PDL") && atoi(getenv("MGB_PDL")) != 0;
+    return on;
+}
+
+template <typename... P, typename... A>
+inline cudaError_t launch_k(void (*kern)(P...), dim3 grid, dim3 block, size_t smem,
+                            cudaStream_t st, A &&...args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    if (pdl_enabled()) {
+        cfg.attrs = at;
+        cfg.numAttrs = 1;
+    }
+    return cudaLaunchKernelEx(&cfg, kern, std::forward<A>(args)...);
+}
+
+// first statement of every kernel launched through launch_k(): let the next
+// kernel's blocks become resident as soon as there is room, then wait until the previous
+// kernel has completed and its writes are visible.  No memory access may precede it.
+__device__ __forceinline__ void pdl_enter()
+{
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
+}  // namespace mgb

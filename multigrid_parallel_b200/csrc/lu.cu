@@ -18,6 +18,7 @@
 #include <cstdio>
 
 #include "kernels.h"
+#include "launch.h"
 #include "lu_band.cuh"
 #include "devmath.cuh"
 
@@ -189,6 +190,7 @@ template <bool LEVEL>
 __global__ void __launch_bounds__(32 * kLuWarps)
 k_lu_band_solve(const LuBand B, const Geo g, const double *__restrict__ rhs, double *__restrict__ x)
 {
+    pdl_enter();
     extern __shared__ double lu_sh[];
     const int n = B.n, npad = (n + 31) & ~31;
     double *xs = lu_sh;
@@ -246,7 +248,7 @@ static void launch_band_solve(const LuBand &B, const Geo &g, const double *rhs, 
                              (int)sh);
         allowed = sh;
     }
-    k_lu_band_solve<LEVEL><<<1, 32 * kLuWarps, sh, st>>>(B, g, rhs, x);
+    launch_k(k_lu_band_solve<LEVEL>, 1, 32 * kLuWarps, sh, st, B, g, rhs, x);
     ++*launch_counter();
 }
 

@@ -53,6 +53,7 @@
 #include <type_traits>
 
 #include "kernels.h"
+#include "launch.h"
 #include "halo.cuh"
 
 namespace mgb {
@@ -218,6 +219,7 @@ __global__ void __launch_bounds__(MINB == 2 ? 384 : 512, MINB == 1 ? 1 : 2)
 k_tile(const TileP P, const __grid_constant__ CUtensorMap tm_v,
        const __grid_constant__ CUtensorMap tm_d)
 {
+    pdl_enter();
     constexpr bool SW = SWEEP >= 0;
     constexpr int HJ = SW ? 1 : 0;    // halo rows / quads recomputed for the sweep
     constexpr int NCOL = SW ? 1 : 2;  // colours carried by the ring
@@ -695,6 +697,7 @@ __global__ void __launch_bounds__(384, 2)
 k_tile_sweep(const TileP P, const __grid_constant__ CUtensorMap tm_v,
              const __grid_constant__ CUtensorMap tm_d)
 {
+    pdl_enter();
     constexpr int S = 4;
     extern __shared__ __align__(128) unsigned char tile_smem[];
     const Geo &g = P.gf;
@@ -896,6 +899,7 @@ __global__ void __launch_bounds__(384, 2)
 k_tile_prolong(const TileP P, const double *__restrict__ ec,
                const __grid_constant__ CUtensorMap tm_v)
 {
+    pdl_enter();
     constexpr int S = 4;
     extern __shared__ __align__(128) unsigned char tile_smem[];
     const Geo &g = P.gf, &gc = P.gc;
@@ -1058,6 +1062,7 @@ __global__ void __launch_bounds__(384, 2)
 k_tile_prolong_one(const TileP P, const double *__restrict__ ec,
                    const __grid_constant__ CUtensorMap tm_v)
 {
+    pdl_enter();
     constexpr int S = 4;
     extern __shared__ __align__(128) unsigned char tile_smem[];
     const Geo &g = P.gf, &gc = P.gc;
@@ -1374,7 +1379,7 @@ bool launch_cfg_b(const TileCfg &c, cudaStream_t st)
     if (!make_tensor_map(&tm_v, c.p.gf, c.p.v, pw, rs, SWEEP >= 0 ? 1 : 2) ||
         !make_tensor_map(&tm_d, c.p.gf, c.p.d, pw, rs, 2))
         return false;
-    k_tile<SWEEP, RESTRICT, MINB, TRT, TQT><<<c.grid, c.threads, c.smem, st>>>(c.p, tm_v, tm_d);
+    launch_k(k_tile<SWEEP, RESTRICT, MINB, TRT, TQT>, c.grid, c.threads, c.smem, st, c.p, tm_v, tm_d);
     ++*launch_counter();
     return true;
 }
@@ -1552,11 +1557,11 @@ bool launch_tile_half_sweep(const Geo &g, double *v, const double *d, double hSq
     }
     const bool fixed = p.TRt == 6 && p.TQt == 43;
     if (colour) {
-        if (fixed) k_tile_sweep<1, 6, 43><<<c.grid, c.threads, c.smem, st>>>(c.p, tm_v, tm_d);
-        else k_tile_sweep<1, 0, 0><<<c.grid, c.threads, c.smem, st>>>(c.p, tm_v, tm_d);
+        if (fixed) launch_k(k_tile_sweep<1, 6, 43>, c.grid, c.threads, c.smem, st, c.p, tm_v, tm_d);
+        else launch_k(k_tile_sweep<1, 0, 0>, c.grid, c.threads, c.smem, st, c.p, tm_v, tm_d);
     } else {
-        if (fixed) k_tile_sweep<0, 6, 43><<<c.grid, c.threads, c.smem, st>>>(c.p, tm_v, tm_d);
-        else k_tile_sweep<0, 0, 0><<<c.grid, c.threads, c.smem, st>>>(c.p, tm_v, tm_d);
+        if (fixed) launch_k(k_tile_sweep<0, 6, 43>, c.grid, c.threads, c.smem, st, c.p, tm_v, tm_d);
+        else launch_k(k_tile_sweep<0, 0, 0>, c.grid, c.threads, c.smem, st, c.p, tm_v, tm_d);
     }
     ++*launch_counter();
     return true;
@@ -1594,9 +1599,9 @@ bool launch_tile_prolong(const Geo &gc, const double *ec, const Geo &gf, double 
             attr1 = true;
         }
         if (cmask == 2)
-            k_tile_prolong_one<1><<<c.grid, c.threads, c.smem, st>>>(c.p, ec, tm1);
+            launch_k(k_tile_prolong_one<1>, c.grid, c.threads, c.smem, st, c.p, ec, tm1);
         else
-            k_tile_prolong_one<0><<<c.grid, c.threads, c.smem, st>>>(c.p, ec, tm1);
+            launch_k(k_tile_prolong_one<0>, c.grid, c.threads, c.smem, st, c.p, ec, tm1);
         ++*launch_counter();
         return true;
     }
@@ -1619,9 +1624,9 @@ bool launch_tile_prolong(const Geo &gc, const double *ec, const Geo &gf, double 
         attr = true;
     }
     if (p.TRt == 6 && p.TQt == 43)
-        k_tile_prolong<6, 43><<<c.grid, c.threads, c.smem, st>>>(c.p, ec, tm_v);
+        launch_k(k_tile_prolong<6, 43>, c.grid, c.threads, c.smem, st, c.p, ec, tm_v);
     else
-        k_tile_prolong<0, 0><<<c.grid, c.threads, c.smem, st>>>(c.p, ec, tm_v);
+        launch_k(k_tile_prolong<0, 0>, c.grid, c.threads, c.smem, st, c.p, ec, tm_v);
     ++*launch_counter();
     return true;
 }

@@ -202,6 +202,12 @@ class Solver:
         check(self.L.mgb_vcycle(self.h_, v))
         return math.sqrt(v.value)
 
+    def vcycles(self, n):
+        """n cycles back to back, one read-back of the last norm (mgb_vcycles)"""
+        v = C.c_double()
+        check(self.L.mgb_vcycles(self.h_, int(n), v))
+        return math.sqrt(v.value)
+
     def fmg_init(self):
         """SolverFMGInitialize (mg_3d.h:1364-1404); returns the residual 2-norm after it"""
         v = C.c_double()

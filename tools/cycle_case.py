@@ -15,6 +15,7 @@ ap.add_argument("--coarse", type=int, nargs=3, default=[3, 3, 3])
 ap.add_argument("--warm", type=int, default=3)
 ap.add_argument("--cycles", type=int, default=2)
 ap.add_argument("--graph", type=int, default=1)
+ap.add_argument("--batch", type=int, default=0, help="1: the timed cycles are enqueued back to back (mgb_vcycles)")
 ap.add_argument("--lu", type=int, default=0, help="N: also time coarse solves of the (2N+1)x9x9 grid")
 a = ap.parse_args()
 with m.Solver(tuple(a.coarse), a.levels, 2) as s:
@@ -26,10 +27,13 @@ with m.Solver(tuple(a.coarse), a.levels, 2) as s:
         s.vcycle()
     s.sync()
     s.timer_start()
-    for _ in range(a.cycles):
-        r = s.vcycle()
+    if a.batch:
+        r = s.vcycles(a.cycles)
+    else:
+        for _ in range(a.cycles):
+            r = s.vcycle()
     dt = s.timer_stop()
-    print(f"grid {s.dims(top)} {1e3 * dt / a.cycles:.3f} ms/cycle, residual {r!r}")
+    print(f"grid {s.dims(top)} {1e3 * dt / a.cycles:.3f} ms/cycle{" (batched)" if a.batch else ""}, residual {r!r}")
 if a.lu:
     with m.Solver((2 * a.lu + 1, 9, 9), 2, 2) as s:
         n, bw, fsec = s.coarse_info()
