@@ -104,6 +104,13 @@ int mgb_set_dirichlet(mgb_solver *s, int level, int which);
  * points of the 12 edges = mean of their two inward neighbours, then the 8 corners
  * = mean of their three edge neighbours.  Unpartitioned levels only. */
 int mgb_edge_values(mgb_solver *s, int level, int which);
+/* GaussSeidelSmoother's sweeps (mg_3d.h:546-634; driver test_gs_3d.c:56): `iters`
+ * LEXICOGRAPHIC Gauss-Seidel sweeps over the interior of u[level] with rhs d[level],
+ * run as a hyperplane wavefront on the GPU -- bit-identical to the reference's serial
+ * (i,j,k) loop.  The reference routine ends with updateEdgeValues: call
+ * mgb_edge_values(s, level, MGB_U) after it for the whole routine.  Unpartitioned
+ * levels only. */
+int mgb_gs_lex(mgb_solver *s, int level, int iters);
 /* single-grid sessions (levels == 1, the raw-pointer API preSmoother / postSmoother /
  * calculateResidual(v, d, N, h, ..) of test_rb_gs_3d.c:56-101): the caller's spacing */
 int mgb_set_spacing(mgb_solver *s, double h);
@@ -227,6 +234,10 @@ int mgb_plan_first_dist_level(int ci, int cj, int ck, int levels, int nranks,
  * back; nothing is computed on the host. */
 int mgb_host_smooth(double *v, const double *d, int ni, int nj, int nk,
                     double h, int iters, int first_red);
+/* GaussSeidelSmoother(v, d, N, h, iters) (mg_3d.h:546-637): lexicographic sweeps and,
+ * with edges != 0, the updateEdgeValues(v, N) that ends the reference routine */
+int mgb_host_gs_lex(double *v, const double *d, int ni, int nj, int nk, double h, int iters,
+                    int edges);
 int mgb_host_residual(const double *v, const double *d, int ni, int nj, int nk,
                       double h, double *res /* may be NULL */, double *sumsq);
 int mgb_host_restrict(const double *r, int nif, int njf, int nkf, double *dc,

@@ -71,6 +71,7 @@ def load_library():
     L.mgb_error_sumsq.argtypes = [vp, c_dp]
     L.mgb_half_sweep.argtypes = [vp, i, i]
     L.mgb_smooth.argtypes = [vp, i, i, i]
+    L.mgb_gs_lex.argtypes = [vp, i, i]
     L.mgb_debug_half_sweep_range.argtypes = [vp, i, i, i, i]
     L.mgb_residual.argtypes = [vp, i, i, c_dp]
     L.mgb_restrict.argtypes = [vp, i]
@@ -101,6 +102,7 @@ def load_library():
     L.mgb_plan_slab.argtypes = [i, i, i, c_ip, c_ip]
     L.mgb_plan_first_dist_level.argtypes = [i, i, i, i, i, i, C.c_longlong]
     L.mgb_host_smooth.argtypes = [c_dp, c_dp, i, i, i, d, i, i]
+    L.mgb_host_gs_lex.argtypes = [c_dp, c_dp, i, i, i, d, i, i]
     L.mgb_host_residual.argtypes = [c_dp, c_dp, i, i, i, d, c_dp, c_dp]
     L.mgb_host_restrict.argtypes = [c_dp, i, i, i, c_dp, i, i, i]
     L.mgb_host_prolong_correct.argtypes = [c_dp, i, i, i, c_dp, i, i, i]

@@ -167,6 +167,20 @@ double BCFunc(double x, double y, double z) { return x * x - 2 * y * y + z * z; 
 
 bool isPowerOfTwo(int x) { return (x & (x - 1)) == 0; }
 
+/* environment + coherence machinery, once per process.  Also reached from the
+ * raw-pointer routines: test_rb_gs_3d.c and test_gs_3d.c never call SolverInitialize. */
+static void mgRuntimeInit(void)
+{
+    static int done = 0;
+    if (done)
+        return;
+    done = 1;
+    const char *e;
+    mgLazySync = (e = getenv("MGB_LAZY_SYNC")) ? atoi(e) != 0 : 1;
+    mgDevice = (e = getenv("MGB_DEVICE")) ? atoi(e) : 0;
+    mgCoherenceInit();
+}
+
 /* ---- set-up (reference mg_3d.h:107-144) ---- */
 void SolverInitialize(int argc, char **argv)
 {
@@ -182,8 +196,7 @@ void SolverInitialize(int argc, char **argv)
     finestOneSideNum = (coarseGridNum - 1) * (1 << (numLevels - 1)) + 1;
 
     const char *e;
-    mgLazySync = (e = getenv("MGB_LAZY_SYNC")) ? atoi(e) != 0 : 1;
-    mgDevice = (e = getenv("MGB_DEVICE")) ? atoi(e) : 0;
+    mgRuntimeInit();
     const int profile = (e = getenv("MGB_PROFILE")) ? atoi(e) != 0 : 1;
 
     u = NULL; d = NULL; r = NULL;
@@ -204,7 +217,6 @@ void SolverInitialize(int argc, char **argv)
     MGB_OK(mgb_create(&mgGpu, coarseGridNum, coarseGridNum, coarseGridNum, numLevels,
                       gsIterNum, mgDevice));
     MGB_OK(mgb_set_option(mgGpu, MGB_OPT_PROFILE, profile));
-    mgCoherenceInit();
     const int top = numLevels - 1;
     const size_t n3 = (size_t)finestOneSideNum * finestOneSideNum * finestOneSideNum;
     /* device arrays start zeroed like the calloc'd host arrays: in sync; from now on the
@@ -314,6 +326,7 @@ static MgSession *mgSessionFor(double *v, const double *dd, int N, double h)
         min_bytes = e ? atoll(e) : (1LL << 20);
     }
     const size_t bytes = (size_t)N * N * N * sizeof(double);
+    mgRuntimeInit();
     if (!mgLazySync || (long long)bytes < min_bytes || v == dd)
         return NULL;
     MgSession *ses = NULL, *spare = NULL;
@@ -502,7 +515,9 @@ void prolongateAndCorrectError(const double *__restrict__ ec, const int Nc,
 
 /* ---- boundary edge/corner averaging and lexicographic Gauss-Seidel ----
  * Not called by the V-cycle (reference call sites are commented out:
- * mg_3d.h:707,779,1281,1340); kept as plain host C so the API is complete. */
+ * mg_3d.h:707,779,1281,1340).  updateEdgeValues on a raw pointer stays host C (O(N)
+ * work; SolverSmoothenEdgeValues uses the device routine); GaussSeidelSmoother runs
+ * on the GPU. */
 void updateEdgeValues(double *__restrict__ v, const int N)
 {
     /* reference mg_3d.h:304-430: each of the 12 edges' inner points becomes the
@@ -534,19 +549,35 @@ void updateEdgeValues(double *__restrict__ v, const int N)
 void GaussSeidelSmoother(double *__restrict__ v, const double *__restrict__ d, const int N,
                          const double h, const int smootherIter)
 {
-    /* reference mg_3d.h:546-637: lexicographic sweep (inherently serial) */
-    const double hSq = h * h, sixth = 1. / 6;
-    const long long NN = (long long)N * N;
-    for (int s = 0; s < smootherIter; s++)
-        for (int i = 1; i < N - 1; i++)
-            for (int j = 1; j < N - 1; j++)
-                for (int k = 1; k < N - 1; k++) {
-                    const long long p = NN * i + (long long)N * j + k;
-                    v[p] = sixth * (v[p - NN] + v[p + NN] + v[p - N] + v[p + N] + v[p - 1] +
-                                    v[p + 1] - hSq * d[p]);
-                }
-    updateEdgeValues(v, N);
-    mgTouchedByHost(v);
+    /* reference mg_3d.h:546-637: smootherIter lexicographic sweeps, then
+     * updateEdgeValues.  On the GPU the serial (i,j,k) order becomes a hyperplane
+     * wavefront (csrc/gslex.cu) with the same bits; like the smoothers above it runs
+     * on the solver's own finest level, on a device-resident session of the caller's
+     * arrays (test_gs_3d.c:56 calls it once per iteration), or staged. */
+#pragma omp single
+    {
+        MG_LOCK();
+        MgSession *ses;
+        if (mgIsFinest(v, d, N) && h == spacing) {
+            mgArrToDevice(mgU);
+            mgArrToDevice(mgD);
+            MGB_OK(mgb_gs_lex(mgGpu, numLevels - 1, smootherIter));
+            MGB_OK(mgb_edge_values(mgGpu, numLevels - 1, MGB_U));
+            MGB_OK(mgb_sync(mgGpu));
+            mgArrDeviceWrote(mgU);
+        } else if ((ses = mgSessionFor(v, d, N, h)) != NULL) {
+            mgArrToDevice(ses->v);
+            mgArrToDevice(ses->d);
+            MGB_OK(mgb_gs_lex(ses->gpu, 0, smootherIter));
+            MGB_OK(mgb_edge_values(ses->gpu, 0, MGB_U));
+            MGB_OK(mgb_sync(ses->gpu));
+            mgArrDeviceWrote(ses->v);
+        } else {
+            const double *dr = mgReadable(d);
+            MGB_OK(mgb_host_gs_lex(mgWritable(v), dr, N, N, N, h, smootherIter, 1));
+        }
+        MG_UNLOCK();
+    }
 }
 
 /* ---- the V-cycle (reference mg_3d.h:1242-1362) ---- */

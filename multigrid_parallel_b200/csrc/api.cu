@@ -1633,6 +1633,27 @@ extern "C" int mgb_smooth(mgb_solver *s, int level, int iters, int first_red)
     return nccl_status();
 }
 
+// GaussSeidelSmoother's sweeps (mg_3d.h:559-634): `iters` LEXICOGRAPHIC Gauss-Seidel
+// sweeps as a hyperplane wavefront (gslex.cu), bit-identical to the serial triple loop
+extern "C" int mgb_gs_lex(mgb_solver *s, int level, int iters)
+{
+    OP_PROLOGUE(level, 0);
+    Level &lv = s->lv[level];
+    if (lv.dist)
+        return fail("mgb_gs_lex: not available on a partitioned level");
+    if (iters < 0)
+        return fail("mgb_gs_lex: iters >= 0");
+    if (level < s->L - 1)
+        s->coarse_dirty = true;
+    // d_scal[15] doubles as the wavefront's arrival counter
+    if (launch_gs_lex(lv.g, lv.a[MGB_U].base, lv.a[MGB_D].base, lv.hSq, iters,
+                      reinterpret_cast<unsigned int *>(s->d_scal + 15), s->st))
+        return fail("mgb_gs_lex: cooperative launch failed: %s",
+                    cudaGetErrorString(cudaGetLastError()));
+    CKLAUNCH();
+    return 0;
+}
+
 extern "C" int mgb_residual(mgb_solver *s, int level, int store_r, double *sumsq)
 {
     OP_PROLOGUE(level, 0);
@@ -2190,6 +2211,31 @@ extern "C" int mgb_host_smooth(double *v, const double *d, int ni, int nj, int n
         launch_half_sweep(tv.g, tv.a.base, td.a.base, hSq, first_red ? 1 : 0, 1, ni - 1, 0);
         launch_half_sweep(tv.g, tv.a.base, td.a.base, hSq, first_red ? 0 : 1, 1, ni - 1, 0);
     }
+    CKLAUNCH();
+    return tmp_download(&tv, v, st.p);
+}
+
+// GaussSeidelSmoother(v, d, N, h, iters) on caller-owned host arrays (test_gs_3d.c:56):
+// the lexicographic sweeps and, with `edges`, the updateEdgeValues that ends the routine
+extern "C" int mgb_host_gs_lex(double *v, const double *d, int ni, int nj, int nk, double h,
+                               int iters, int edges)
+{
+    if (host_ready())
+        return 1;
+    Tmp tv, td;
+    Scratch st, bar;
+    if (tmp_make(&tv, ni, nj, nk) || tmp_make(&td, ni, nj, nk))
+        return 1;
+    CK(cudaMalloc(&st.p, sizeof(double) * (size_t)ni * nj * nk));
+    CK(cudaMalloc(&bar.p, sizeof(double)));
+    if (tmp_upload(&tv, v, st.p) || tmp_upload(&td, d, st.p))
+        return 1;
+    if (launch_gs_lex(tv.g, tv.a.base, td.a.base, h * h, iters,
+                      reinterpret_cast<unsigned int *>(bar.p), 0))
+        return fail("mgb_host_gs_lex: cooperative launch failed: %s",
+                    cudaGetErrorString(cudaGetLastError()));
+    if (edges)
+        launch_edge_values(tv.g, tv.a.base, 0);
     CKLAUNCH();
     return tmp_download(&tv, v, st.p);
 }

@@ -31,6 +31,12 @@ void launch_half_sweep(const Geo &g, double *v, const double *d, double hSq,
                        int colour, int il_lo, int il_hi, cudaStream_t st,
                        const HaloCtl *h = nullptr);
 
+// GaussSeidelSmoother's lexicographic sweeps as a hyperplane wavefront (gslex.cu,
+// mg_3d.h:546-637); whole levels only; `bar` = one unsigned int of device scratch;
+// non-zero: the cooperative launch failed
+int launch_gs_lex(const Geo &g, double *v, const double *d, double hSq, int iters,
+                  unsigned int *bar, cudaStream_t st);
+
 // the same when every neighbour is known to be zero (first sweep of a coarse level)
 void launch_first_sweep_zero(const Geo &g, double *v, const double *d, double hSq, int colour,
                              int il_lo, int il_hi, cudaStream_t st, const HaloCtl *h = nullptr);

@@ -157,6 +157,10 @@ class Solver:
     def smooth(self, level, iters, first_red):
         check(self.L.mgb_smooth(self.h_, level, iters, int(first_red)))
 
+    def gs_lex(self, level, iters):
+        """`iters` lexicographic Gauss-Seidel sweeps (GaussSeidelSmoother, mg_3d.h:546-634)"""
+        check(self.L.mgb_gs_lex(self.h_, level, iters))
+
     def residual(self, level, store_r=False):
         """returns sqrt(sum of squares) like calculateResidual on one thread"""
         v = C.c_double()
@@ -254,6 +258,12 @@ def set_global(key, value):
 def host_smooth(v, d, h, iters, first_red):
     L = load_library()
     check(L.mgb_host_smooth(_dp(v), _dp(d), *v.shape, h, iters, int(first_red)))
+
+
+def host_gs_lex(v, d, h, iters, edges=True):
+    """GaussSeidelSmoother(v, d, N, h, iters) on host arrays (mg_3d.h:546-637)"""
+    L = load_library()
+    check(L.mgb_host_gs_lex(_dp(v), _dp(d), *v.shape, h, iters, int(edges)))
 
 
 def host_residual(v, d, h, res=None):

@@ -113,6 +113,10 @@ def main():
     A = ref.coarse_matrix(5, 0.25); ops["coarse_matrix_5"] = sha(A)
     ref.lu_factor(A); ops["lu_5"] = sha(A)
     b = seeded((125,), 3); ops["lu_solve_5"] = sha(ref.lu_solve(A, b))
+    # GaussSeidelSmoother (mg_3d.h:546-637: lexicographic sweeps + updateEdgeValues), the
+    # reference's own symbol, on the same seeded inputs
+    w = v.copy(); ref.gs_lex(w, d, h, 2); ops["gauss_seidel_smoother_2"] = sha(w)
+    ref.gs_lex(w, d, h, 1); ops["then_gauss_seidel_smoother_1"] = sha(w)
     json.dump(ops, open(os.path.join(GOLD, "operators.json"), "w"), indent=1)
     print("operators.json written")
 

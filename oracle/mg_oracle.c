@@ -64,6 +64,56 @@ void orc_smooth(double *v, const double *d, int ni, int nj, int nk, double h,
     }
 }
 
+void orc_edge_values(double *v, int ni, int nj, int nk)
+{
+    /* updateEdgeValues (mg_3d.h:304-430) for a box: the inner points of the 12 edges
+     * become the mean of their two inward neighbours (311-397: the four edges along j
+     * and along k of the X faces, then the four along i -- an edge point reads only
+     * face-interior points, so the order among edges is immaterial), then each of the 8
+     * corners the mean of its three edge neighbours, added in k, j, i order (399-429). */
+    const i64 s[3] = {(i64)nj * nk, nk, 1};
+    const int n[3] = {ni, nj, nk};
+    for (int fa = 0; fa < 3; fa++) { /* axis along the edge */
+        const int b = (fa + 1) % 3, c = (fa + 2) % 3;
+        for (int eb = 0; eb < 2; eb++)
+            for (int ec = 0; ec < 2; ec++) {
+                const i64 inb = eb ? -s[b] : s[b], inc = ec ? -s[c] : s[c];
+                for (int t = 1; t < n[fa] - 1; t++) {
+                    const i64 p = t * s[fa] + (eb ? n[b] - 1 : 0) * s[b] + (ec ? n[c] - 1 : 0) * s[c];
+                    v[p] = 0.5 * (v[p + inb] + v[p + inc]);
+                }
+            }
+    }
+    for (int ei = 0; ei < 2; ei++)
+        for (int ej = 0; ej < 2; ej++)
+            for (int ek = 0; ek < 2; ek++) {
+                const i64 p = (ei ? ni - 1 : 0) * s[0] + (ej ? nj - 1 : 0) * s[1] + (ek ? nk - 1 : 0);
+                const i64 ini = ei ? -s[0] : s[0], inj = ej ? -s[1] : s[1], ink = ek ? -1 : 1;
+                v[p] = (1. / 3) * (v[p + ink] + v[p + inj] + v[p + ini]);
+            }
+}
+
+void orc_gs_lex(double *v, const double *d, int ni, int nj, int nk, double h, int iters,
+                int edges)
+{
+    /* GaussSeidelSmoother (mg_3d.h:546-637): `iters` lexicographic sweeps (559-634: the
+     * same point formula as smoothenAtIndex, points visited in ascending (i,j,k), each
+     * update visible to the next), then updateEdgeValues (635). */
+    const double hSq = h * h;
+    const double sixth = 1. / 6;
+    const i64 sj = nk, si = (i64)nj * nk;
+    for (int s = 0; s < iters; s++)
+        for (int i = 1; i < ni - 1; i++)
+            for (int j = 1; j < nj - 1; j++)
+                for (int k = 1; k < nk - 1; k++) {
+                    i64 p = IDX(i, j, k);
+                    v[p] = sixth * (v[p - si] + v[p + si] + v[p - sj] + v[p + sj] +
+                                    v[p - 1] + v[p + 1] - hSq * d[p]);
+                }
+    if (edges)
+        orc_edge_values(v, ni, nj, nk);
+}
+
 double orc_residual(const double *v, const double *d, int ni, int nj, int nk,
                     double h, double *res)
 {

@@ -34,6 +34,11 @@ void orc_smooth(double *v, const double *d, int ni, int nj, int nk, double h,
                 int iters, int first_red);
 
 /* one colour only: colour 1 = red = (i+j+k) odd, 0 = black (mg_3d.h:669-693) */
+/* GaussSeidelSmoother (mg_3d.h:546-637): lexicographic sweeps (+ updateEdgeValues) */
+void orc_gs_lex(double *v, const double *d, int ni, int nj, int nk, double h, int iters,
+                int edges);
+/* updateEdgeValues (mg_3d.h:304-430) for a box */
+void orc_edge_values(double *v, int ni, int nj, int nk);
 void orc_half_sweep(double *v, const double *d, int ni, int nj, int nk,
                     double h, int colour);
 

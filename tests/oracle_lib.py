@@ -49,6 +49,8 @@ class Orc:
         L.orc_set_dirichlet.argtypes = [p, i, i, i, d]
         L.orc_smooth.argtypes = [p, p, i, i, i, d, i, i]
         L.orc_half_sweep.argtypes = [p, p, i, i, i, d, i]
+        L.orc_gs_lex.argtypes = [p, p, i, i, i, d, i, i]
+        L.orc_edge_values.argtypes = [p, i, i, i]
         L.orc_residual.restype = d
         L.orc_residual.argtypes = [p, p, i, i, i, d, p]
         L.orc_restrict.argtypes = [p, i, i, i, p, i, i, i]
@@ -84,6 +86,13 @@ class Orc:
 
     def half_sweep(self, v, d, h, colour):
         self.L.orc_half_sweep(_p(v), _p(d), *v.shape, h, colour)
+
+    def gs_lex(self, v, d, h, iters, edges=True):
+        """GaussSeidelSmoother (mg_3d.h:546-637)"""
+        self.L.orc_gs_lex(_p(v), _p(d), *v.shape, h, iters, int(edges))
+
+    def edge_values(self, v):
+        self.L.orc_edge_values(_p(v), *v.shape)
 
     def residual(self, v, d, h, res=None):
         return self.L.orc_residual(_p(v), _p(d), *v.shape, h, _p(res))
@@ -185,6 +194,8 @@ class Ref:
         L.ref_max_threads.restype = i
         L.ref_set_dirichlet.argtypes = [p, i, d]
         L.ref_smooth.argtypes = [p, p, i, d, i, i]
+        L.GaussSeidelSmoother.argtypes = [p, p, i, d, i]  # the reference's own symbol
+        L.updateEdgeValues.argtypes = [p, i]
         L.ref_residual.restype = d
         L.ref_residual.argtypes = [p, p, i, d, p]
         L.ref_restrict.argtypes = [p, i, p, i]
@@ -218,6 +229,13 @@ class Ref:
 
     def smooth(self, v, d, h, iters, first_red):
         self.L.ref_smooth(_p(v), _p(d), v.shape[0], h, iters, int(first_red))
+
+    def gs_lex(self, v, d, h, iters):
+        """the reference's GaussSeidelSmoother (sweeps + updateEdgeValues), cubes only"""
+        self.L.GaussSeidelSmoother(_p(v), _p(d), v.shape[0], h, iters)
+
+    def edge_values(self, v):
+        self.L.updateEdgeValues(_p(v), v.shape[0])
 
     def residual(self, v, d, h, res=None):
         return self.L.ref_residual(_p(v), _p(d), v.shape[0], h, _p(res))

@@ -60,7 +60,17 @@ def main():
                      f"| warp insts {float(vals['warp_insts'][0])/1e6:.1f} M")
         key = re.sub(r"<.*", "", name) if name.startswith("k_half_sweep") else name
         seen.setdefault(key, []).append((rd + wr, float(vals["time_us"][0]), vals["grid"][0]))
+    def blocks(grid):
+        n = 1
+        for x in re.findall(r"\d+", grid):
+            n *= int(x)
+        return n
+
     for key, lst in seen.items():
+        # one template instance serves several levels: keep the launches of the largest
+        # grid (the finest level), so that the figures are per FINEST-level launch
+        most = max(blocks(x[2]) for x in lst)
+        lst = [x for x in lst if blocks(x[2]) == most]
         traffic[key] = {"dram_bytes_per_launch": sum(x[0] for x in lst) / len(lst),
                         "ncu_time_us": sum(x[1] for x in lst) / len(lst), "launches": len(lst),
                         "grid": lst[0][2], "source": os.path.basename(out)}
