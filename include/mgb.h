@@ -219,7 +219,7 @@ int mgb_nccl_unique_id(void *out128);
 int mgb_create_dist(mgb_solver **out, int ci, int cj, int ck, int levels,
                     int gs_iters, int device, int rank, int nranks,
                     const void *nccl_uid128, int min_planes_per_rank,
-                    long long min_points_per_rank /* < 0: default 2^20 */);
+                    long long min_points_per_rank /* < 0: default 2^22 / nranks */);
 int mgb_dist_info(const mgb_solver *s, int *rank, int *nranks, int *first_dist_level);
 int mgb_local_range(const mgb_solver *s, int level, int *i0, int *li, int *own_lo,
                     int *own_hi);

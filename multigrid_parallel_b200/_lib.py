@@ -15,7 +15,8 @@ class MgbError(RuntimeError):
 
 
 def lib_path():
-    return os.path.join(_HERE, "libmgb.so")
+    # MGB_LIB: another build of the same library (A/B timing of a kernel variant)
+    return os.environ.get("MGB_LIB") or os.path.join(_HERE, "libmgb.so")
 
 
 def header_path():

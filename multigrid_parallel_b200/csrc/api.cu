@@ -718,7 +718,9 @@ extern "C" int mgb_create_dist(mgb_solver **out, int ci, int cj, int ck, int lev
     if (nranks & (nranks - 1))
         return fail("nranks must be a power of two (got %d)", nranks);
     // defaults: a level is partitioned while every rank owns >= 2 planes (an even number)
-    // and the level as a whole has >= 2^20 points; the levels below are replicated:
+    // and the level as a whole has >= 2^22 points (8 GPUs, round 2: 1025^3 strong 4.686 ms
+    // with 129^3 partitioned, 4.663 replicated; weak 4.144 -> 4.127); the levels below are
+    // replicated:
     // computed redundantly on every rank from an all-gathered right-hand side.  Measured on
     // 2 B200s: a half-sweep on a slab of a small level costs kernel + ~7 us of flag latency
     // (every step has to hear from the neighbour), the same kernel on the whole level ~4 us
@@ -728,7 +730,7 @@ extern "C" int mgb_create_dist(mgb_solver **out, int ci, int cj, int ck, int lev
     return create_impl(out, ci, cj, ck, levels, gs_iters, device, rank, nranks, nccl_uid128,
                        min_planes_per_rank > 0 ? min_planes_per_rank : 2,
                        min_points_per_rank >= 0 ? min_points_per_rank
-                                                : (1LL << 20) / (nranks > 0 ? nranks : 1));
+                                                : (1LL << 22) / (nranks > 0 ? nranks : 1));
 }
 
 extern "C" int mgb_dist_info(const mgb_solver *s, int *rank, int *nranks, int *first_dist_level)
