@@ -248,6 +248,25 @@ int mgb_host_coarse_matrix(double *A, int ni, int nj, int nk, double h);
 int mgb_host_lu_factor(double *a, int n);
 int mgb_host_lu_solve(const double *lu, int n, const double *b, double *x);
 
+/* ---- writeOutputData (postprocess.h:5-47) with the text produced on the GPU -----------
+ * The reference's ASCII legacy-VTK file of a grid of ni x nj x nk values (k fastest) and
+ * spacing h, as a stream of byte chunks: header, one "%10.8e %10.8e %10.8e\n" line per
+ * point, the POINT_DATA header, one "%10.8e\n" line per value.  Concatenated, the chunks
+ * are byte for byte what the reference's fprintf loop writes (csrc/vtk.cu: exact decimal
+ * conversion on the device; the few values whose rounding the device cannot decide with
+ * certainty make their chunk fall back to the C library's snprintf).  `values` is a host
+ * array that must stay readable until mgb_vtk_close.  Usage:
+ *     mgb_vtk_open(&w, grid, N, N, N, h, 0);
+ *     while (!mgb_vtk_next(w, &p, &n) && n) fwrite(p, 1, n, file);
+ *     mgb_vtk_close(w);
+ * A chunk stays valid until the next mgb_vtk_next / mgb_vtk_close on the same writer. */
+typedef struct mgb_vtk mgb_vtk;
+int mgb_vtk_open(mgb_vtk **w, const double *values, int ni, int nj, int nk, double h,
+                 int device);
+int mgb_vtk_next(mgb_vtk *w, const char **bytes, long long *n);
+int mgb_vtk_host_chunks(const mgb_vtk *w, long long *chunks);
+int mgb_vtk_close(mgb_vtk *w);
+
 /* ---- resident single-grid session for the RB-GS microbenchmark
  * (test_rb_gs_3d.c flow: one grid, no hierarchy).  A 1-level solver:
  * mgb_create(.., levels=1, ..) gives u/d/r on the finest grid only and no

@@ -104,6 +104,10 @@ def load_library():
     L.mgb_plan_first_dist_level.argtypes = [i, i, i, i, i, i, C.c_longlong]
     L.mgb_host_smooth.argtypes = [c_dp, c_dp, i, i, i, d, i, i]
     L.mgb_host_gs_lex.argtypes = [c_dp, c_dp, i, i, i, d, i, i]
+    L.mgb_vtk_open.argtypes = [C.POINTER(vp), c_dp, i, i, i, d, i]
+    L.mgb_vtk_next.argtypes = [vp, C.POINTER(C.c_char_p), C.POINTER(C.c_longlong)]
+    L.mgb_vtk_host_chunks.argtypes = [vp, C.POINTER(C.c_longlong)]
+    L.mgb_vtk_close.argtypes = [vp]
     L.mgb_host_residual.argtypes = [c_dp, c_dp, i, i, i, d, c_dp, c_dp]
     L.mgb_host_restrict.argtypes = [c_dp, i, i, i, c_dp, i, i, i]
     L.mgb_host_prolong_correct.argtypes = [c_dp, i, i, i, c_dp, i, i, i]

@@ -299,7 +299,8 @@ def dropin_e2e(device):
     secs = float(re.search(r"^Overall time for solving:\s*(\S+)", p.stdout, re.M).group(1))
     cycles = len(re.findall(r"Residual Norm:", p.stdout))
     err = re.search(r"^Error norm:\s*(\S+)", p.stdout, re.M).group(1)
-    vtk = re.search(r"writeOutputData .*: 513\^3 points, (\d+) threads, ([0-9.]+) s", p.stderr)
+    vtk = re.search(r"writeOutputData .*: 513\^3 points, formatted on the GPU \((\d+) chunks by the "
+                    r"host's snprintf\), ([0-9.]+) s", p.stderr)
     dof = 513.0 ** 3
     return {"program": "the reference's unmodified test_mg_3d.c on compat/mg_3d.h, args 3 9 2, "
                        f"{threads} OpenMP threads, MGB_PROFILE=1 (per-stage timing, eager launches), "
@@ -308,5 +309,8 @@ def dropin_e2e(device):
             "value": dof * cycles / secs, "unit": "DOF*cycles/s",
             "error_norm_printed": err, "whole_program_wall_s": wall,
             "vtk_formatting_s": float(vtk.group(2)) if vtk else None,
-            "vtk_note": "ASCII legacy VTK of 513^3 points (8 GB) formatted in parallel on the host, "
-                        "byte-identical to the reference's writer, written to /dev/null"}
+            "vtk_chunks_formatted_by_host_snprintf": int(vtk.group(1)) if vtk else None,
+            "vtk_note": "ASCII legacy VTK of 513^3 points (8 GB): text produced on the GPU "
+                        "(mgb_vtk_*, exact decimal conversion), streamed through pinned buffers, "
+                        "byte-identical to the reference's writer, written to /dev/null; the "
+                        "reference's fprintf loop takes ~2.5 min for the same file"}

@@ -31,6 +31,15 @@ static int fail(const char *fmt, ...)
     return 1;
 }
 
+// for the other translation units of the library (vtk.cu)
+namespace mgb {
+int set_error(const char *msg)
+{
+    g_err = msg;
+    return 1;
+}
+}  // namespace mgb
+
 #define CK(call)                                                                  \
     do {                                                                          \
         cudaError_t e_ = (call);                                                  \

@@ -11,11 +11,14 @@
 // those of a plain stream.  Transitively safe: kernel N cannot complete before its own
 // threads return from their wait, i.e. before kernel N-1 has completed.
 // The attribute survives stream capture (programmatic edges in the graph).
-// Measured on B200 (round 2, tools/cycle_case.py --batch 1, 513^3 ... 9^3 hierarchies): no
-// difference beyond run-to-run noise (3.695 vs 3.678 ms at 513^3, 0.212 vs 0.214 ms at
-// 129^3) -- the small kernels are bound by their own first-load latency and drain, which a
-// wait at the top cannot overlap -- so it is OFF by default; MGB_PDL=1 turns it on
-// (pdl_enter() is a no-op in hardware for a plain launch).
+// Measured on B200 (round 2): inside the graph-replayed cycle no difference beyond
+// run-to-run noise (tools/cycle_case.py --batch 1: 3.695 vs 3.678 ms at 513^3, 0.212 vs
+// 0.214 ms at 129^3 -- the small kernels are bound by their own first-load latency and
+// drain, which a wait at the top cannot overlap); on back-to-back eager launches of
+// mid-sized kernels it hides the launch gap: RB-GS at 257^3 (tools/bench_rbgs.py) 77.95 ->
+// 74.66 us per full sweep.  ON by default; MGB_PDL=0 gives plain launches (pdl_enter()
+// is then a no-op in hardware).  The TMA half-sweep kernel waits only after its
+// shared-memory set-up (pdl_trigger() / pdl_wait() apart).
 #pragma once
 #include <cuda_runtime.h>
 
@@ -26,7 +29,7 @@ namespace mgb {
 
 inline bool pdl_enabled()
 {
-    static const bool on = getenv("MGB_PDL") && atoi(getenv("MGB_PDL")) != 0;
+    static const bool on = !(getenv("MGB_PDL") && atoi(getenv("MGB_PDL")) == 0);
     return on;
 }
 
@@ -52,10 +55,18 @@ inline cudaError_t launch_k(void (*kern)(P...), dim3 grid, dim3 block, size_t sm
 // first statement of every kernel launched through launch_k(): let the next
 // kernel's blocks become resident as soon as there is room, then wait until the previous
 // kernel has completed and its writes are visible.  No memory access may precede it.
-__device__ __forceinline__ void pdl_enter()
+__device__ __forceinline__ void pdl_trigger()
 {
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+__device__ __forceinline__ void pdl_wait()
+{
     asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+__device__ __forceinline__ void pdl_enter()
+{
+    pdl_trigger();
+    pdl_wait();
 }
 
 }  // namespace mgb

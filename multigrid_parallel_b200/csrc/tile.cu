@@ -697,7 +697,7 @@ __global__ void __launch_bounds__(384, 2)
 k_tile_sweep(const TileP P, const __grid_constant__ CUtensorMap tm_v,
              const __grid_constant__ CUtensorMap tm_d)
 {
-    pdl_enter();
+    pdl_trigger();  // the wait follows the shared-memory set-up (nothing global before it)
     constexpr int S = 4;
     extern __shared__ __align__(128) unsigned char tile_smem[];
     const Geo &g = P.gf;
@@ -716,8 +716,10 @@ k_tile_sweep(const TileP P, const __grid_constant__ CUtensorMap tm_v,
     const int kmax = g.nk - 2;
     const int ia = P.p_lo + tile_chunk(P) * P.chunk;
     const int ib = min(ia + P.chunk, P.p_hi);
-    if (ia >= ib)
+    if (ia >= ib) {
+        pdl_wait();
         return;
+    }
     const int pr0 = ia - 1, plast = ib;
     const uint32_t ring_u32 = smem_u32(ring), bars_u32 = smem_u32(bars);
     const uint32_t box_bytes = (uint32_t)(RS * PW) * 8u, slot_bytes = (uint32_t)slot_d * 8u;
@@ -728,6 +730,7 @@ k_tile_sweep(const TileP P, const __grid_constant__ CUtensorMap tm_v,
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
+    pdl_wait();
     halo_wait_cta(P.h, ia == P.p_lo, ib == P.p_hi);
     // planes of this chunk whose new values also go into a neighbour's halo
     const HaloPush &hu = P.h.push_up, &hl = P.h.push_low;
@@ -1212,7 +1215,8 @@ int tile_max_threads();
 // Number of plane chunks (grid.z).  Measured on B200 (513^3, 1025^3): chunks of
 // about 52 fine planes are best -- 341-plane chunks at 1025^3 cost 10-20 %,
 // 24-plane chunks at 513^3 2-4 % (each chunk re-reads 2-4 planes to start up) --
-// as long as the launch still has >= 4 blocks per resident slot; never fewer
+// as long as the launch still has >= 4 blocks per resident slot (MGB_TILE_FILL; 6 cost the
+// 257^2-plane half-sweep 1.4 %: 21 chunks of 12 planes instead of 14 of 18); never fewer
 // than `minchunk` fine planes per chunk (12: a 64-plane slab of 513^2 planes -- one rank's
 // share of that level of 1025^3 on 8 GPUs -- takes 38.6 us in 5 chunks, 49.1 us in the 2
 // chunks a minimum of 24 allows).  `unit` = fine planes per counted plane.
@@ -1220,7 +1224,7 @@ int plan_chunks(int nplanes, int unit, long long per_layer, int minchunk)
 {
     static const int target = env_int("MGB_TILE_CHUNK", 52);
     long long want = ((long long)nplanes * unit + target / 2) / target;
-    const long long fill = ((long long)env_int("MGB_TILE_FILL", 6) * 296 + per_layer - 1) / per_layer;
+    const long long fill = ((long long)env_int("MGB_TILE_FILL", 4) * 296 + per_layer - 1) / per_layer;
     if (want < fill)
         want = fill;
     long long maxch = (long long)nplanes * unit / minchunk;
@@ -1529,7 +1533,7 @@ bool launch_tile_half_sweep(const Geo &g, double *v, const double *d, double hSq
     // (6.5 TB/s = 99 % of the measured copy peak), 1025^3 2.21 vs 2.24 ms, but
     // 257^3 43.6 vs 41.4 us: planes of >= 200k points only
     static const int on = env_int("MGB_TILE_SWEEP", 1);
-    static const long long min_plane = env_int("MGB_TILE_SWEEP_MIN_PLANE", 200000);
+    static const long long min_plane = env_int("MGB_TILE_SWEEP_MIN_PLANE", 60000);
     if (!on || !tile_enabled() || il_hi - il_lo < 8 || !tile_worthwhile(g) ||
         ((long long)g.nj * g.nk < min_plane && g_tile_min_plane > 0))
         return false;

@@ -266,6 +266,36 @@ def host_gs_lex(v, d, h, iters, edges=True):
     check(L.mgb_host_gs_lex(_dp(v), _dp(d), *v.shape, h, iters, int(edges)))
 
 
+def vtk_stream(values, h, device=0):
+    """writeOutputData (postprocess.h:5-47) through mgb_vtk_*: yields the byte chunks of the
+    reference's ASCII VTK file for the grid `values` (shape (ni, nj, nk)); the generator's
+    `host_chunks` attribute is not available -- use vtk_bytes for the count"""
+    L = load_library()
+    w = C.c_void_p()
+    check(L.mgb_vtk_open(C.byref(w), _dp(values), *values.shape, h, device))
+    try:
+        p = C.c_void_p()
+        n = C.c_longlong()
+        nxt = L.mgb_vtk_next
+        nxt.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_longlong)]
+        while True:
+            check(nxt(w, C.byref(p), C.byref(n)))
+            if n.value == 0:
+                break
+            yield C.string_at(p.value, n.value)
+        hc = C.c_longlong()
+        check(L.mgb_vtk_host_chunks(w, C.byref(hc)))
+        vtk_stream.last_host_chunks = hc.value
+    finally:
+        check(L.mgb_vtk_close(w))
+
+
+def vtk_bytes(values, h, device=0):
+    """the whole file; returns (bytes, number of chunks the host's snprintf had to format)"""
+    data = b"".join(vtk_stream(values, h, device))
+    return data, vtk_stream.last_host_chunks
+
+
 def host_residual(v, d, h, res=None):
     L = load_library()
     ss = C.c_double()

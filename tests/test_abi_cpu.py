@@ -138,6 +138,7 @@ def test_compat_host_helpers_match_reference(tmp_path, ref):
     ref.set_dirichlet(b, h)
     assert np.array_equal(a, b)
     L.writeOutputData.argtypes = [C.c_char_p, c_dp, C.c_double, C.c_int]
+    os.environ["MGB_VTK_GPU"] = "0"  # the host formatter (the GPU one: tests/test_gpu_vtk.py)
     f1 = tmp_path / "a.vtk"
     L.writeOutputData(str(f1).encode(), a.ctypes.data_as(c_dp), h, N)
     # reference writer: not in libmg_ref (postprocess.h is not included there);

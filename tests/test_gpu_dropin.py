@@ -92,10 +92,11 @@ def test_reference_driver_unmodified_513(tmp_path):
     secs = float(re.search(r"^Overall time for solving:\s*(\S+)", p.stdout, re.M).group(1))
     assert 0 < secs < 60
     assert p.stdout.count("LEVEL ") == 9
-    vtk = re.search(r"writeOutputData .*: 513\^3 points, (\d+) threads, ([0-9.]+) s", p.stderr)
+    vtk = re.search(r"writeOutputData .*: 513\^3 points, formatted on the GPU \((\d+) chunks by the "
+                    r"host's snprintf\), ([0-9.]+) s", p.stderr)
     assert vtk, p.stderr[-500:]
     print(f"test_mg_3d 3 9 2 on the drop-in: Overall time for solving {secs:.4f} s, "
-          f"VTK formatting {vtk.group(2)} s on {vtk.group(1)} threads")
+          f"VTK text on the GPU in {vtk.group(2)} s ({vtk.group(1)} chunks by the host)")
 
 
 def test_reference_driver_usage_error(tmp_path):
