@@ -347,9 +347,14 @@ def run_ours(args):
     strong = None if args.no_extras else _leg(B.strong1025, world, rank, local_rank)
     c5 = None if args.no_extras else _leg(B.config5, world)
 
-    dropin = None
+    dropin = next_rows = None
     if world == 1 and not args.no_extras:
         dropin = _leg(B.dropin_e2e, local_rank)
+        # SURVEY 8(f) rows built after the hot path: measured, not part of the metric
+        next_rows = {"f1_fmg": _leg(B.fmg_cycles, local_rank),
+                     "f2_vtk_gpu": _leg(B.vtk_stream, 257, local_rank),
+                     "f4_gs_lex": {"257": _leg(B.gs_lex, 257, local_rank),
+                                   "513": _leg(B.gs_lex, 513, local_rank)}}
 
     cpu = None
     if rank == 0 and not args.no_cpu_baseline:
@@ -393,6 +398,8 @@ def run_ours(args):
             line["config5"] = c5
         if dropin is not None:
             line["e2e_dropin"] = dropin
+        if next_rows is not None:
+            line["next_rows"] = next_rows
         print(json.dumps(line), flush=True)
     D.barrier()
     return 0

@@ -195,6 +195,60 @@ def rbgs(n, iters, device):
             "bytes_per_dof_per_full_sweep": 24.0, "residual_after": res}
 
 
+def gs_lex(n, device, reps=3):
+    """GaussSeidelSmoother's lexicographic sweep (mg_3d.h:546-637,
+    test_gs_3d.c:56 flow: one sweep per call on a resident grid) as a hyperplane wavefront"""
+    with Solver(n, 1, 1, device=device) as s:
+        s.set_dirichlet(0, MGB_U)
+        s.gs_lex(0, 1)
+        s.sync()
+        s.timer_start()
+        for _ in range(reps):
+            s.gs_lex(0, 1)
+        sec = s.timer_stop() / reps
+    return {"grid": f"{n}^3", "ms_per_sweep": 1e3 * sec, "dof_per_s": float(n) ** 3 / sec,
+            "hyperplane_steps": 3 * n - 8,
+            "note": "bit-identical to the serial (i,j,k) loop; latency-bound (one grid-wide "
+                    "barrier per hyperplane), not HBM-bound"}
+
+
+def fmg_cycles(device):
+    """cycles to 1e-8*||d|| at 513^3 with and without SolverFMGInitialize
+    (mg_3d.h:1364-1404 as written: it amounts to one V-cycle ahead)"""
+    out = {}
+    for use in (False, True):
+        with Solver(3, 9, 2, device=device) as s:
+            init = fresh_problem(s)
+            n = 0
+            r = None
+            if use:
+                r = s.fmg_init()
+            while (r is None or r > 1e-8 * init) and n < 60:
+                r = s.vcycle()
+                n += 1
+            out["with_fmg_init" if use else "plain"] = {"cycles_to_1e-8": n, "final_residual": r}
+    return out
+
+
+def vtk_stream(n, device):
+    """writeOutputData's file for an n^3 grid produced on the GPU and
+    streamed to the host (mgb_vtk_*): seconds and bytes, chunks discarded as they arrive"""
+    import numpy as np
+    from .solver import vtk_stream as stream
+    rng = np.random.default_rng(0)
+    v = rng.uniform(-1e-6, 1e-6, (n, n, n))
+    t0 = time.perf_counter()
+    nbytes = 0
+    for chunk in stream(v, 1.0 / (n - 1), device):
+        nbytes += len(chunk)
+    sec = time.perf_counter() - t0
+    return {"grid": f"{n}^3", "bytes": nbytes, "seconds": sec, "gb_per_s": nbytes / sec / 1e9,
+            "chunks_formatted_by_host_snprintf": stream.last_host_chunks,
+            "note": "text produced on the device, byte-identical to postprocess.h:5-47; includes "
+                    "H2D of the values (pageable), D2H of the text and a copy of every chunk "
+                    "into Python bytes"}
+
+
 def _cycle_ms(coarse, levels, gs, steps, warmup, solve=True, device=None, single=False):
     """ms per V-cycle of a fresh test_mg_3d-type problem on the current ranks (or, with
     single=True, on this process's GPU alone)"""
