@@ -74,7 +74,10 @@ int mgb_set_option(mgb_solver *s, int key, int value);
  * graphs already built keep what they captured) */
 enum {
     MGB_G_TILE = 0,           /* 1 (default): TMA tile kernels for residual / residual+restrict */
-    MGB_G_TILE_MIN_PLANE = 1  /* use them on levels with nj*nk >= value (default 40000)         */
+    MGB_G_TILE_MIN_PLANE = 1, /* use them on levels with nj*nk >= value (default 40000)         */
+    MGB_G_GSLEX_TILE = 2      /* mgb_gs_lex kernel: 1 (default) by level size, 0 global
+                                 hyperplanes, 2..5 force the tile wavefront with tiles of
+                                 8x16x32, 8x8x32, 8x32x32, 16x16x32 points */
 };
 int mgb_set_global(int key, long long value);
 /* the launch plan the TMA tile kernels would use on an ni x nj x nk level, without

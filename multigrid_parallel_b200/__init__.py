@@ -10,11 +10,11 @@ from .solver import (  # noqa: F401
     MGB_D, MGB_R, MGB_U, STAGE_NAMES, Solver, host_coarse_matrix, host_lu_factor,
     host_lu_solve, host_prolong_correct, host_residual, host_restrict, host_smooth,
     host_gs_lex, vtk_bytes, vtk_stream,
-    set_global, G_TILE, G_TILE_MIN_PLANE,
+    set_global, G_TILE, G_TILE_MIN_PLANE, G_GSLEX_TILE,
 )
 
 __all__ = [
     "Solver", "MgbError", "load_library", "lib_path", "MGB_U", "MGB_D", "MGB_R",
-    "STAGE_NAMES", "set_global", "G_TILE", "G_TILE_MIN_PLANE", "host_smooth", "host_gs_lex", "vtk_bytes", "vtk_stream", "host_residual", "host_restrict",
+    "STAGE_NAMES", "set_global", "G_TILE", "G_TILE_MIN_PLANE", "G_GSLEX_TILE", "host_smooth", "host_gs_lex", "vtk_bytes", "vtk_stream", "host_residual", "host_restrict",
     "host_prolong_correct", "host_coarse_matrix", "host_lu_factor", "host_lu_solve",
 ]

@@ -832,6 +832,7 @@ extern "C" int mgb_set_global(int key, long long value)
     switch (key) {
     case MGB_G_TILE: tile_set(value != 0, -1); break;
     case MGB_G_TILE_MIN_PLANE: tile_set(-1, value < 0 ? 0 : value); break;
+    case MGB_G_GSLEX_TILE: gs_lex_set_mode((int)value); break;
     default: return fail("unknown global option %d", key);
     }
     return 0;

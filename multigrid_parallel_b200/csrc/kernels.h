@@ -36,6 +36,8 @@ void launch_half_sweep(const Geo &g, double *v, const double *d, double hSq,
 // non-zero: the cooperative launch failed
 int launch_gs_lex(const Geo &g, double *v, const double *d, double hSq, int iters,
                   unsigned int *bar, cudaStream_t st);
+// kernel selection of launch_gs_lex (MGB_G_GSLEX_TILE, env MGB_GSLEX_TILE)
+void gs_lex_set_mode(int mode);
 
 // the same when every neighbour is known to be zero (first sweep of a coarse level)
 void launch_first_sweep_zero(const Geo &g, double *v, const double *d, double hSq, int colour,

@@ -246,7 +246,7 @@ class Solver:
         return self.L.mgb_launch_count(self.h_)
 
 
-G_TILE, G_TILE_MIN_PLANE = 0, 1
+G_TILE, G_TILE_MIN_PLANE, G_GSLEX_TILE = 0, 1, 2
 
 
 def set_global(key, value):

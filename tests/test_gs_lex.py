@@ -95,11 +95,23 @@ def test_wavefront_schedule_equals_serial_sweep(orc, shape, iters):
 
 
 # ---------------------------------------------------------------- GPU
+LEX_MODES = {"auto": 1, "hyperplanes": 0, "t8x16x32": 2, "t8x8x32": 3, "t8x32x32": 4, "t16x16x32": 5}
+
+
+@pytest.fixture(params=list(LEX_MODES))
+def lex_kernel(request, mgb):
+    """every GPU test of the sweep runs with the kernel the library would pick and with
+    each kernel forced (global hyperplanes, the tile wavefront in four tile shapes)"""
+    mgb.set_global(mgb.G_GSLEX_TILE, LEX_MODES[request.param])
+    yield request.param
+    mgb.set_global(mgb.G_GSLEX_TILE, 1)
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("coarse,levels", [((3, 3, 3), 5), ((5, 5, 5), 3), ((3, 5, 9), 3),
                                            ((9, 3, 5), 2), ((3, 3, 3), 6)])
 @pytest.mark.parametrize("iters", [1, 2, 5])
-def test_gpu_gs_lex_bitwise(mgb, orc, coarse, levels, iters):
+def test_gpu_gs_lex_bitwise(mgb, orc, lex_kernel, coarse, levels, iters):
     with mgb.Solver(coarse, levels, 2) as s:
         for lvl in range(levels):
             shape = s.dims(lvl)
@@ -119,9 +131,9 @@ def test_gpu_gs_lex_bitwise(mgb, orc, coarse, levels, iters):
 
 
 @pytest.mark.gpu
-def test_gpu_gs_lex_large_plane_many_blocks(mgb, orc):
+def test_gpu_gs_lex_large_plane_many_blocks(mgb, orc, lex_kernel):
     """a level whose hyperplanes need every SM's block (grid-wide barrier path)"""
-    with mgb.Solver((257, 129, 5), 1, 1) as s:
+    with mgb.Solver((257, 129, 37), 1, 1) as s:
         shape = s.dims(0)
         v, d = seeded(shape, 5), seeded(shape, 6)
         s.upload(0, mgb.MGB_U, v)

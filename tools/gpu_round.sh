@@ -1,3 +1,6 @@
 mkdir -p gpurun_out
-R=r02v
-python -m pytest tests/test_gpu_vtk.py tests/test_gpu_dropin.py tests/test_gs_lex.py -m gpu -x -q -s > gpurun_out/${R}_pytest.log 2>&1; echo "pytest rc $?" >> gpurun_out/${R}_pytest.log; grep -v "^$" gpurun_out/${R}_pytest.log | tail -25
+R=r02z
+timeout 600 python -m pytest tests/test_gs_lex.py -m gpu -x -q > gpurun_out/${R}_pytest.log 2>&1; echo "pytest rc $?" >> gpurun_out/${R}_pytest.log; tail -4 gpurun_out/${R}_pytest.log
+L=gpurun_out/${R}_gslex.log; rm -f $L
+for mode in 2 3 4 5; do echo "== MGB_GSLEX_TILE=$mode" >> $L; MGB_GSLEX_TILE=$mode timeout 300 python tools/bench_gslex.py --n 65 129 257 513 >> $L 2>&1; done
+cat $L
