@@ -352,7 +352,7 @@ def run_ours(args):
         dropin = _leg(B.dropin_e2e, local_rank)
         # SURVEY 8(f) rows built after the hot path: measured, not part of the metric
         next_rows = {"f1_fmg": _leg(B.fmg_cycles, local_rank),
-                     "f2_vtk_gpu": _leg(B.vtk_stream, 257, local_rank),
+                     "f2_vtk_gpu": _leg(B.vtk_stream, 513, local_rank),
                      "f4_gs_lex": {"257": _leg(B.gs_lex, 257, local_rank),
                                    "513": _leg(B.gs_lex, 513, local_rank)}}
 
