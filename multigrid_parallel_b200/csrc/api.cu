@@ -11,6 +11,7 @@
 
 #include "../../include/mgb.h"
 #include "kernels.h"
+#include "launch.h"
 #include "nccl_dl.h"
 
 using namespace mgb;
@@ -536,6 +537,7 @@ static int create_impl(mgb_solver **out, int ci, int cj, int ck, int levels, int
             delete s;
             return fail("a partitioned solver needs at least 2 levels");
         }
+        pdl_dist_active() = true;  // launch.h: plain launches in a process with peers
         s->LD = mgb_plan_first_dist_level(ci, cj, ck, levels, nranks, min_planes, min_points);
         if (s->LD >= levels) {
             delete s;

@@ -100,15 +100,6 @@ __device__ __forceinline__ void halo_st_release(unsigned long long *p, unsigned 
     asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
-__device__ __forceinline__ void halo_st_relaxed(unsigned long long *p, unsigned long long v)
-{
-    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-__device__ __forceinline__ void halo_fence_sys()
-{
-    asm volatile("fence.acq_rel.sys;" ::: "memory");
-}
-
 // spin until *flag >= target; gives up after timeout_ns (sets the error bit, returns)
 static __device__ __noinline__ void halo_spin(const unsigned long long *flag, unsigned long long target,
                                        unsigned long long timeout_ns, unsigned int *err,
@@ -168,20 +159,19 @@ __device__ __forceinline__ void halo_signal_cta(const HaloCtl &h, const HaloPush
     // grid-wide barrier), so ONE system-scope fence per CTA makes them all visible ...
     __syncthreads();
     if (threadIdx.x == 0) {
-        halo_fence_sys();  // release pattern: my CTA's peer stores, then my arrival
+        __threadfence_system();
         const unsigned int prev = atomicAdd(p.count, 1u);
         if (prev == p.nblocks - 1) {  // ... and the last CTA to get here has seen all of them
             *p.count = 0;
-            // ONE fence closes the acquire pattern (arrival RMW, fence) and opens the release
-            // pattern (fence, relaxed flag store); round 2's first version fenced here and
-            // then used st.release.sys, i.e. two more system-scope fences on the critical
-            // path of every half-sweep of a partitioned level (A/B on 2 GPUs, same box:
-            // 3.943 -> 3.919 ms per weak-scaling cycle)
-            if (p.nblocks > 1)
-                halo_fence_sys();
-            halo_st_relaxed(p.peer_flag, *h.epoch * kHaloEpochStride + p.off);
+            __threadfence_system();
+            halo_st_release(p.peer_flag, *h.epoch * kHaloEpochStride + p.off);
         }
     }
+    // Round 2 tried to shorten this (fence.acq_rel.sys instead of the sc fences, one fence and
+    // a relaxed flag store in the last CTA): 0.6 % faster on 2 GPUs and WRONG on 8 -- with
+    // the consumer's CTAs already resident (programmatic dependent launch) the flag overtook
+    // peer stores of the CTA's other warps (tests/dist_check.py, 65^3 over 8 ranks: norm off
+    // in the 4th digit after cycle 2; either change alone passed).  The sc fences stay.
 }
 
 // a smoother's store of the pair (r0, r1) at in-plane offset `off` of local plane `plane`,

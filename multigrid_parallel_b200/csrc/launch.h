@@ -16,8 +16,8 @@
 // 0.214 ms at 129^3 -- the small kernels are bound by their own first-load latency and
 // drain, which a wait at the top cannot overlap); on back-to-back eager launches of
 // mid-sized kernels it hides the launch gap: RB-GS at 257^3 (tools/bench_rbgs.py) 77.95 ->
-// 74.66 us per full sweep.  ON by default; MGB_PDL=0 gives plain launches (pdl_enter()
-// is then a no-op in hardware).  The TMA half-sweep kernel waits only after its
+// 74.66 us per full sweep.  ON by default in single-GPU processes; MGB_PDL=0 gives plain
+// launches (pdl_enter() is then a no-op in hardware).  The TMA half-sweep kernel waits only after its
 // shared-memory set-up (pdl_trigger() / pdl_wait() apart).
 #pragma once
 #include <cuda_runtime.h>
@@ -27,10 +27,20 @@
 
 namespace mgb {
 
+// a partitioned solver exists in this process: its kernels also synchronise with PEER GPUs
+// through flags in memory, PDL buys them nothing measurable (2 GPUs: 3.891 vs 3.873 ms per
+// cycle) and makes every latent ordering weakness visible (halo.cuh) -- plain launches there
+// unless MGB_PDL=1 insists
+inline bool &pdl_dist_active()
+{
+    static bool active = false;
+    return active;
+}
+
 inline bool pdl_enabled()
 {
-    static const bool on = !(getenv("MGB_PDL") && atoi(getenv("MGB_PDL")) == 0);
-    return on;
+    static const int mode = getenv("MGB_PDL") ? atoi(getenv("MGB_PDL")) : -1;
+    return mode < 0 ? !pdl_dist_active() : mode != 0;
 }
 
 template <typename... P, typename... A>

@@ -32,6 +32,10 @@ def main():
         ((3, 3, 3), 8, 2, 16, -1, 2, False),     # 257^3 with the default thresholds
         ((3, 3, 3), 8, 2, 0, -1, 3, False),      # 257^3, everything default
     ]
+    # DIST_CHECK_CASES=0,2 / DIST_CHECK_REPEAT=5: a subset, several times (hunting a race)
+    if os.environ.get("DIST_CHECK_CASES"):
+        cases = [cases[int(x)] for x in os.environ["DIST_CHECK_CASES"].split(",")]
+    cases = cases * int(os.environ.get("DIST_CHECK_REPEAT", "1"))
     for min_plane in (40000, 0):  # default kernel choice, then TMA tile kernels on every level
         m.set_global(m.G_TILE_MIN_PLANE, min_plane)
         for case in cases:
