@@ -40,6 +40,7 @@
 
 #include "devmath.cuh"
 #include "kernels.h"
+#include "launch.h"
 
 namespace mgb {
 
@@ -300,11 +301,9 @@ int launch_lex_tile(const Geo &g, double *v, const double *d, double hSq, int it
                reinterpret_cast<unsigned int *>(scratch + items_b),
                reinterpret_cast<unsigned int *>(scratch + items_b) + ntiles};
     constexpr size_t sh = sizeof(double) * ((size_t)(TI + 2) * (TJ + 2) * (TK + 2) + (size_t)TI * TJ * (TK + 2));
-    static bool attr = false;
-    if (!attr) {
+    static unsigned long long attr_seen = 0;
+    if (first_on_device(attr_seen))
         cudaFuncSetAttribute(k_gs_lex_tile<TI, TJ, TK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh);
-        attr = true;
-    }
     static int sms = 0, per_sm = 0;
     if (!sms) {
         int dev = 0;

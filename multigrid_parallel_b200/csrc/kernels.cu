@@ -901,12 +901,10 @@ void launch_residual_restrict(const Geo &gf, const double *vf, const double *df,
     const unsigned bx = (gc.nj + TY - 1) / TY;
     const int nplanes = Il_hi - Il_lo;
     const size_t sh = sizeof(double) * 2 * R * (4 * npair + 2);
-    static bool attr_set = false;
-    if (!attr_set) {
+    static unsigned long long attr_seen = 0;
+    if (first_on_device(attr_seen))
         cudaFuncSetAttribute(k_residual_restrict<1024>,
                              cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
-        attr_set = true;
-    }
     const int occ = resident_blocks(k_residual_restrict<1024>, threads, sh);
     const int nch = pick_chunks(bx, nplanes, occ);
     const int chunk = (nplanes + nch - 1) / nch;

@@ -43,6 +43,34 @@ inline bool pdl_enabled()
     return mode < 0 ? !pdl_dist_active() : mode != 0;
 }
 
+// cudaFuncSetAttribute acts on the CURRENT device: call sites remember per device what they
+// have set (a process may hold solvers on several GPUs)
+inline bool first_on_device(unsigned long long &seen)
+{
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64)
+        return true;
+    if ((seen >> dev) & 1ull)
+        return false;
+    seen |= 1ull << dev;
+    return true;
+}
+// the same for an attribute that grows with the request (dynamic shared memory)
+inline bool grows_on_device(size_t (&allowed)[64], size_t want)
+{
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64)
+        return want > 48 * 1024;
+    if (allowed[dev] == 0)
+        allowed[dev] = 48 * 1024;
+    if (want <= allowed[dev])
+        return false;
+    allowed[dev] = want;
+    return true;
+}
+
 template <typename... P, typename... A>
 inline cudaError_t launch_k(void (*kern)(P...), dim3 grid, dim3 block, size_t smem,
                             cudaStream_t st, A &&...args)

@@ -242,12 +242,10 @@ static void launch_band_solve(const LuBand &B, const Geo &g, const double *rhs, 
                               cudaStream_t st)
 {
     const size_t sh = sizeof(double) * lu_solve_smem_doubles(B.n) + 16;
-    static size_t allowed = 48 * 1024;
-    if (sh > allowed) {
+    static size_t allowed[64] = {};
+    if (grows_on_device(allowed, sh))
         cudaFuncSetAttribute(k_lu_band_solve<LEVEL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              (int)sh);
-        allowed = sh;
-    }
     launch_k(k_lu_band_solve<LEVEL>, 1, 32 * kLuWarps, sh, st, B, g, rhs, x);
     ++*launch_counter();
 }

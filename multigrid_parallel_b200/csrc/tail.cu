@@ -385,11 +385,9 @@ void launch_coarse_tail(const TailP &p, cudaStream_t st)
     const size_t need = tail_smem_bytes(p);
     q.smem = whole && !no_smem && need <= (size_t)smem_limit;
     const size_t sh = q.smem ? need : 0;
-    static size_t allowed = 48 * 1024;
-    if (sh > allowed) {
+    static size_t allowed[64] = {};
+    if (grows_on_device(allowed, sh))
         cudaFuncSetAttribute(k_coarse_tail, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sh);
-        allowed = sh;
-    }
     if (p.lu.n <= 32 && whole) {
         q.phase = 0;
         launch_k(k_coarse_tail, 1, kTailThreads, sh, st, q);

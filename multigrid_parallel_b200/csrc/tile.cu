@@ -1371,13 +1371,11 @@ int tile_max_threads() { return tile_bps() == 2 ? 384 : 512; }
 template <int SWEEP, bool RESTRICT, int MINB, int TRT = 0, int TQT = 0>
 bool launch_cfg_b(const TileCfg &c, cudaStream_t st)
 {
-    static bool attr = false;
-    if (!attr) {
+    static unsigned long long attr_seen = 0;
+    if (first_on_device(attr_seen))
         cudaFuncSetAttribute(k_tile<SWEEP, RESTRICT, MINB, TRT, TQT>,
                              cudaFuncAttributeMaxDynamicSharedMemorySize,
                              MINB == 1 ? 226 * 1024 : 112 * 1024);
-        attr = true;
-    }
     const int rs = c.p.TRt + 2, pw = 2 * (c.p.TQt + 2);
     CUtensorMap tm_v, tm_d;
     if (!make_tensor_map(&tm_v, c.p.gf, c.p.v, pw, rs, SWEEP >= 0 ? 1 : 2) ||
@@ -1551,13 +1549,12 @@ bool launch_tile_half_sweep(const Geo &g, double *v, const double *d, double hSq
     if (!make_tensor_map(&tm_v, g, v, (int)PW, (int)RS, 1) ||
         !make_tensor_map(&tm_d, g, d, (int)PW, (int)RS, 1))
         return false;
-    static bool attr = false;
-    if (!attr) {
+    static unsigned long long attr_seen = 0;
+    if (first_on_device(attr_seen)) {
         cudaFuncSetAttribute(k_tile_sweep<0, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024);
         cudaFuncSetAttribute(k_tile_sweep<1, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024);
         cudaFuncSetAttribute(k_tile_sweep<0, 6, 43>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024);
         cudaFuncSetAttribute(k_tile_sweep<1, 6, 43>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024);
-        attr = true;
     }
     const bool fixed = p.TRt == 6 && p.TQt == 43;
     if (colour) {
@@ -1596,11 +1593,10 @@ bool launch_tile_prolong(const Geo &gc, const double *ec, const Geo &gf, double 
         CUtensorMap tm1;
         if (!make_tensor_map(&tm1, gf, ef, (int)PW, (int)RS, 1))
             return false;
-        static bool attr1 = false;
-        if (!attr1) {
+        static unsigned long long attr1_seen = 0;
+        if (first_on_device(attr1_seen)) {
             cudaFuncSetAttribute(k_tile_prolong_one<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024);
             cudaFuncSetAttribute(k_tile_prolong_one<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024);
-            attr1 = true;
         }
         if (cmask == 2)
             launch_k(k_tile_prolong_one<1>, c.grid, c.threads, c.smem, st, c.p, ec, tm1);
@@ -1621,11 +1617,10 @@ bool launch_tile_prolong(const Geo &gc, const double *ec, const Geo &gf, double 
     CUtensorMap tm_v;
     if (!make_tensor_map(&tm_v, gf, ef, (int)PW, (int)RS, cmask == 3 ? 2 : 1))
         return false;
-    static bool attr = false;
-    if (!attr) {
+    static unsigned long long attr_seen = 0;
+    if (first_on_device(attr_seen)) {
         cudaFuncSetAttribute(k_tile_prolong<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024);
         cudaFuncSetAttribute(k_tile_prolong<6, 43>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024);
-        attr = true;
     }
     if (p.TRt == 6 && p.TQt == 43)
         launch_k(k_tile_prolong<6, 43>, c.grid, c.threads, c.smem, st, c.p, ec, tm_v);

@@ -94,6 +94,83 @@ def test_wavefront_schedule_equals_serial_sweep(orc, shape, iters):
     assert np.array_equal(v, w)
 
 
+def tile_schedule_model(v, d, h, iters, tile, workers, seed):
+    """the TILE-level schedule of k_gs_lex_tile in Python: work items (sweep, a, b, c) are
+    handed out by a ticket counter in the order of a+b+c+2*sweep; a worker that holds an
+    item runs it only once the flags say so -- the three "minus" tiles at this sweep, the
+    three "plus" tiles and the tile itself at the previous one -- and otherwise waits while
+    other workers (picked at random) go on.  A tile is swept lexicographically from the
+    array as it is at that moment.  Returns the number of scheduling steps."""
+    ni, nj, nk = v.shape
+    TI, TJ, TK = tile
+    nt = [-(-(n - 2) // t) for n, t in zip((ni, nj, nk), tile)]
+    items = sorted(((s, a, b, c) for s in range(iters) for a in range(nt[0])
+                    for b in range(nt[1]) for c in range(nt[2])),
+                   key=lambda w: w[1] + w[2] + w[3] + 2 * w[0])
+    done = np.zeros(nt, dtype=int)
+    rng = np.random.default_rng(seed)
+    hSq, sixth = h * h, 1.0 / 6
+    ticket, holding, steps, running = 0, {}, 0, set()
+
+    def ready(s, a, b, c):
+        for axis in range(3):
+            for plus in (0, 1):
+                n = [a, b, c]
+                n[axis] += 1 if plus else -1
+                if 0 <= n[axis] < nt[axis] and done[tuple(n)] < (s if plus else s + 1):
+                    return False
+        return done[a, b, c] >= s
+
+    while ticket < len(items) or holding:
+        for wk in range(workers):  # idle workers draw tickets, in worker order
+            if wk not in holding and ticket < len(items):
+                holding[wk] = items[ticket]
+                ticket += 1
+        # items are in flight for a while: starting one must never find the same tile or a
+        # face neighbour still being worked on (that is what makes a tile's sweep atomic)
+        startable = [wk for wk, it in holding.items() if wk not in running and ready(*it)]
+        if startable and (not running or rng.integers(2)):
+            wk = startable[rng.integers(len(startable))]
+            _, a, b, c = holding[wk]
+            for other in running:
+                _, a2, b2, c2 = holding[other]
+                assert abs(a - a2) + abs(b - b2) + abs(c - c2) > 1, "overlapping tiles in flight"
+            running.add(wk)
+            continue
+        assert running, "deadlock: every worker waits"
+        wk = sorted(running)[rng.integers(len(running))]
+        running.discard(wk)
+        s, a, b, c = holding.pop(wk)
+        for i in range(1 + a * TI, min(1 + (a + 1) * TI, ni - 1)):
+            for j in range(1 + b * TJ, min(1 + (b + 1) * TJ, nj - 1)):
+                for k in range(1 + c * TK, min(1 + (c + 1) * TK, nk - 1)):
+                    t = v[i - 1, j, k] + v[i + 1, j, k]
+                    t = t + v[i, j - 1, k]
+                    t = t + v[i, j + 1, k]
+                    t = t + v[i, j, k - 1]
+                    t = t + v[i, j, k + 1]
+                    v[i, j, k] = sixth * (t - hSq * d[i, j, k])
+        done[a, b, c] = s + 1
+        steps += 1
+    return steps
+
+
+@pytest.mark.parametrize("shape,tile,iters,workers", [((9, 8, 11), (2, 3, 4), 3, 4),
+                                                      ((6, 6, 6), (8, 8, 8), 4, 3),   # one tile
+                                                      ((12, 5, 7), (3, 2, 2), 2, 16),
+                                                      ((5, 13, 6), (1, 4, 2), 3, 2)])
+def test_tile_schedule_equals_serial_sweep(orc, shape, tile, iters, workers):
+    """whatever order the flags allow, the ticket-ordered tile wavefront gives the serial
+    result, and no set of workers can end up waiting for each other"""
+    h = 0.21
+    for seed in range(3):
+        v, d = seeded(shape, 75), seeded(shape, 76)
+        w = v.copy()
+        orc.gs_lex(v, d, h, iters, edges=False)
+        tile_schedule_model(w, d, h, iters, tile, workers, seed)
+        assert np.array_equal(v, w), (shape, tile, seed)
+
+
 # ---------------------------------------------------------------- GPU
 LEX_MODES = {"auto": 1, "hyperplanes": 0, "t8x16x32": 2, "t8x8x32": 3, "t8x32x32": 4, "t16x16x32": 5}
 
