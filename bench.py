@@ -92,8 +92,9 @@ def workload_config(n_gpus):
                         f"test_mg_3d 3 9 2 stretched along i: 512 planes of 513^2 per GPU), Dirichlet "
                         f"x^2-2y^2+z^2, coarse {2 * n_gpus + 1}x3x3 LU, {LEVELS} levels, stopping rule "
                         "1e-8*||d||",
-            "parallelism": f"i-slabs over {n_gpus} GPUs (one process per GPU), halo planes over NVLink "
-                           "peer memory, coarse levels below the partitioning threshold on one GPU",
+            "parallelism": f"i-slabs over {n_gpus} GPUs (one process per GPU), halo planes stored into "
+                           "the neighbours' memory over NVLink by the compute kernels, coarse levels "
+                           "below the partitioning threshold replicated on every GPU (P2P all-gather)",
             "l2": "inputs larger than L2 (3 x 1.1 GB level arrays per GPU vs 126 MB)"}
 
 

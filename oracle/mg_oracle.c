@@ -8,6 +8,7 @@
 #include "mg_oracle.h"
 
 #include <math.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -292,6 +293,33 @@ void orc_lu_solve(const double *lu, int n, const double *b, double *x)
             s += row[c] * x[c];
         x[r] = (x[r] - s) / row[r];
     }
+}
+
+int orc_write_vtk(const char *path, const double *grid, int ni, int nj, int nk, double h)
+{
+    /* writeOutputData (postprocess.h:5-47) for a box: header (13-19), one line of
+     * coordinates h*i, h*j, h*k per point with k fastest (22-33), the POINT_DATA header
+     * (36-41), one value per line (42-44); every number through "%10.8e" */
+    FILE *f = fopen(path, "w");
+    if (!f)
+        return 1;
+    const long total = (long)ni * nj * nk;
+    fprintf(f, "# vtk DataFile Version 2.0\nPotential data\nASCII\nDATASET STRUCTURED_GRID\n"
+               "DIMENSIONS %d %d %d\nPOINTS %d float\n", ni, nj, nk, (int)total);
+    for (int i = 0; i < ni; i++) {
+        double x = h * i;
+        for (int j = 0; j < nj; j++) {
+            double y = h * j;
+            for (int k = 0; k < nk; k++) {
+                double z = h * k;
+                fprintf(f, "%10.8e %10.8e %10.8e\n", x, y, z);
+            }
+        }
+    }
+    fprintf(f, "\nPOINT_DATA %d\nSCALARS data float 1\nLOOKUP_TABLE default\n", (int)total);
+    for (long c = 0; c < total; c++)
+        fprintf(f, "%10.8e\n", grid[c]);
+    return fclose(f) != 0;
 }
 
 double orc_l2norm(const double *d, long n)

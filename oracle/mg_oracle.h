@@ -64,6 +64,8 @@ void orc_lu_solve(const double *lu, int n, const double *b, double *x);
 
 /* mg_3d.h:783-792 */
 double orc_l2norm(const double *d, long n);
+/* writeOutputData (postprocess.h:5-47) for a box; non-zero on I/O failure */
+int orc_write_vtk(const char *path, const double *grid, int ni, int nj, int nk, double h);
 
 /* ---- multilevel driver (mg_3d.h:107-144, 275-293, 1242-1362) ---- */
 typedef struct orc_mg orc_mg;

@@ -14,6 +14,7 @@
 
 #define GRID_LENGTH (1.)
 #include "mg_3d.h"
+#include "postprocess.h"
 
 void ref_set_threads(int n) { omp_set_num_threads(n); }
 int ref_max_threads(void) { return omp_get_max_threads(); }
@@ -246,4 +247,10 @@ static int solve_flow(int coarse, int levels, int gs, double tol, int max_cycles
         memcpy(u_out, grid, sizeof(double) * (size_t)N * N * N);
     ref_solver_close();
     return c;
+}
+
+/* the reference's own VTK writer (postprocess.h:5-47), cubes only */
+void ref_write_vtk(const char *path, const double *grid, double h, int N)
+{
+    writeOutputData(path, grid, h, N);
 }

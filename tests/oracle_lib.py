@@ -58,6 +58,8 @@ class Orc:
         L.orc_coarse_matrix.argtypes = [p, i, i, i, d]
         L.orc_lu_factor.argtypes = [p, i]
         L.orc_lu_solve.argtypes = [p, i, p, p]
+        L.orc_write_vtk.restype = i
+        L.orc_write_vtk.argtypes = [C.c_char_p, p, i, i, i, d]
         L.orc_l2norm.restype = d
         L.orc_l2norm.argtypes = [p, C.c_long]
         L.orc_mg_create.restype = C.c_void_p
@@ -119,6 +121,10 @@ class Orc:
 
     def l2norm(self, d):
         return self.L.orc_l2norm(_p(d), d.size)
+
+    def write_vtk(self, path, grid, h):
+        """writeOutputData (postprocess.h:5-47) for a box"""
+        assert self.L.orc_write_vtk(str(path).encode(), _p(grid), *grid.shape, h) == 0
 
 
 class OrcMG:
@@ -203,6 +209,8 @@ class Ref:
         L.ref_coarse_matrix.argtypes = [p, i, d]
         L.ref_lu_factor.argtypes = [p, i]
         L.ref_lu_solve.argtypes = [p, i, p, p]
+        if hasattr(L, "ref_write_vtk"):
+            L.ref_write_vtk.argtypes = [C.c_char_p, p, d, i]
         L.ref_l2norm.restype = d
         L.ref_l2norm.argtypes = [p, i]
         L.ref_solve.restype = i
@@ -236,6 +244,10 @@ class Ref:
 
     def edge_values(self, v):
         self.L.updateEdgeValues(_p(v), v.shape[0])
+
+    def write_vtk(self, path, grid, h):
+        """the reference's own writeOutputData (postprocess.h:5-47), cubes only"""
+        self.L.ref_write_vtk(str(path).encode(), _p(grid), h, grid.shape[0])
 
     def residual(self, v, d, h, res=None):
         return self.L.ref_residual(_p(v), _p(d), v.shape[0], h, _p(res))

@@ -117,3 +117,13 @@ L.writeOutputData({str(tmp_path / "host.vtk")!r}.encode(), v.ctypes.data_as(c_dp
     assert "formatted on the GPU" in p.stderr
     a, b = (tmp_path / "gpu.vtk").read_bytes(), (tmp_path / "host.vtk").read_bytes()
     assert a == b and len(a) > 21 ** 3 * 60
+
+
+def test_vtk_stream_equals_the_oracle_file(mgb, orc, tmp_path):
+    """the device-formatted stream against the file oracle/mg_oracle.c writes (which the CPU
+    suite pins to the reference's own writeOutputData)"""
+    shape = (21, 34, 19)
+    v = seeded(shape, 41) * 10.0 ** np.random.default_rng(2).integers(-14, 2, shape)
+    orc.write_vtk(tmp_path / "o.vtk", v, 1 / 32)
+    data, host_chunks = mgb.vtk_bytes(v, 1 / 32)
+    assert data == (tmp_path / "o.vtk").read_bytes() and host_chunks == 0

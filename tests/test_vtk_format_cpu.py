@@ -157,3 +157,32 @@ def test_model_near_decimal_boundaries():
         x = float(f"1e{E}")
         for y in (x, np.nextafter(x, np.inf), np.nextafter(x, -np.inf)):
             check(float(y), allow_exception=True)
+
+
+def test_oracle_vtk_writer_vs_compiled_reference(tmp_path, orc, ref):
+    """oracle/mg_oracle.c: orc_write_vtk against the reference's own writeOutputData
+    (postprocess.h:5-47, compiled into oracle/_ref), byte for byte"""
+    if ref is None or not hasattr(ref.L, "ref_write_vtk"):
+        import pytest
+        pytest.skip("oracle/_ref not built")
+    from oracle_lib import seeded
+    for N, seed in ((5, 1), (9, 2), (17, 3)):
+        v = seeded((N,) * 3, seed) * 10.0 ** np.random.default_rng(seed).integers(-12, 3, (N,) * 3)
+        v[0, 0, :3] = [0.0, -0.0, 103 / 1024]
+        h = 1.0 / (N - 1)
+        a, b = tmp_path / f"orc{N}.vtk", tmp_path / f"ref{N}.vtk"
+        orc.write_vtk(a, v, h)
+        ref.write_vtk(b, v, h)
+        assert a.read_bytes() == b.read_bytes()
+
+
+def test_oracle_vtk_writer_lines(tmp_path, orc):
+    """... and, for a box, against the format strings themselves"""
+    from oracle_lib import seeded
+    v = seeded((3, 4, 5), 8)
+    orc.write_vtk(tmp_path / "box.vtk", v, 0.25)
+    lines = (tmp_path / "box.vtk").read_text().split("\n")
+    assert lines[4] == "DIMENSIONS 3 4 5" and lines[5] == "POINTS 60 float"
+    assert lines[6 + 7] == "%10.8e %10.8e %10.8e" % (0.0, 0.25 * 1, 0.25 * 2)  # point 7 = (0, 1, 2)
+    assert lines[6 + 60:6 + 64] == ["", "POINT_DATA 60", "SCALARS data float 1", "LOOKUP_TABLE default"]
+    assert lines[6 + 64 + 59] == "%10.8e" % v.reshape(-1)[59] and lines[-1] == ""
