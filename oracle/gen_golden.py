@@ -117,6 +117,12 @@ def main():
     # reference's own symbol, on the same seeded inputs
     w = v.copy(); ref.gs_lex(w, d, h, 2); ops["gauss_seidel_smoother_2"] = sha(w)
     ref.gs_lex(w, d, h, 1); ops["then_gauss_seidel_smoother_1"] = sha(w)
+    # writeOutputData (postprocess.h:5-47), the reference's own writer, on a seeded 9^3 grid
+    import tempfile
+    g = seeded((9,) * 3, 21) * 10.0 ** np.random.default_rng(21).integers(-12, 3, (9,) * 3)
+    with tempfile.TemporaryDirectory() as tmp:
+        ref.write_vtk(os.path.join(tmp, "g.vtk"), g, 0.125)
+        ops["vtk_9_sha256"] = hashlib.sha256(open(os.path.join(tmp, "g.vtk"), "rb").read()).hexdigest()
     json.dump(ops, open(os.path.join(GOLD, "operators.json"), "w"), indent=1)
     print("operators.json written")
 

@@ -127,3 +127,12 @@ def test_vtk_stream_equals_the_oracle_file(mgb, orc, tmp_path):
     orc.write_vtk(tmp_path / "o.vtk", v, 1 / 32)
     data, host_chunks = mgb.vtk_bytes(v, 1 / 32)
     assert data == (tmp_path / "o.vtk").read_bytes() and host_chunks == 0
+
+
+def test_vtk_stream_golden(mgb):
+    """... and against the hash of the reference's own file for the seeded 9^3 grid"""
+    import json
+    ops = json.load(open(os.path.join(HERE, "golden", "operators.json")))
+    g = seeded((9,) * 3, 21) * 10.0 ** np.random.default_rng(21).integers(-12, 3, (9,) * 3)
+    data, host_chunks = mgb.vtk_bytes(g, 0.125)
+    assert hashlib.sha256(data).hexdigest() == ops["vtk_9_sha256"] and host_chunks == 0

@@ -186,3 +186,15 @@ def test_oracle_vtk_writer_lines(tmp_path, orc):
     assert lines[6 + 7] == "%10.8e %10.8e %10.8e" % (0.0, 0.25 * 1, 0.25 * 2)  # point 7 = (0, 1, 2)
     assert lines[6 + 60:6 + 64] == ["", "POINT_DATA 60", "SCALARS data float 1", "LOOKUP_TABLE default"]
     assert lines[6 + 64 + 59] == "%10.8e" % v.reshape(-1)[59] and lines[-1] == ""
+
+
+def test_oracle_vtk_writer_golden(tmp_path, orc):
+    """hash of the file the reference's own writer produced for a seeded 9^3 grid
+    (tests/golden/operators.json, oracle/gen_golden.py)"""
+    import hashlib
+    import json
+    from oracle_lib import seeded
+    ops = json.load(open(os.path.join(ROOT, "tests", "golden", "operators.json")))
+    g = seeded((9,) * 3, 21) * 10.0 ** np.random.default_rng(21).integers(-12, 3, (9,) * 3)
+    orc.write_vtk(tmp_path / "g.vtk", g, 0.125)
+    assert hashlib.sha256((tmp_path / "g.vtk").read_bytes()).hexdigest() == ops["vtk_9_sha256"]

@@ -1,3 +1,2 @@
 mkdir -p gpurun_out
-R=r02F
-python -m pytest tests -m gpu -x -q > gpurun_out/${R}_pytest.log 2>&1; echo "pytest rc $?" >> gpurun_out/${R}_pytest.log; tail -3 gpurun_out/${R}_pytest.log
+python -m pytest tests/test_gpu_vtk.py -m gpu -x -q > gpurun_out/r02G_pytest.log 2>&1; echo "pytest rc $?" >> gpurun_out/r02G_pytest.log; tail -3 gpurun_out/r02G_pytest.log
