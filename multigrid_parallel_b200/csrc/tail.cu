@@ -247,7 +247,8 @@ __device__ void t_lu_small(const LuBand &B, const SL &L0, int lane)
 // phase 0: the whole sub-cycle (solve included, n <= 32); phase 1: the down leg (levels
 // top .. 1) and the zero guess of level 0; phase 2: the up leg (levels 1 .. top), with the
 // stand-alone solve kernel (lu.cu) launched in between.
-__global__ void __launch_bounds__(kTailThreads) k_coarse_tail(const TailP P)
+// (min blocks = 1 spelled out: without it ptxas stops at 64 registers and spills the solve's tile)
+__global__ void __launch_bounds__(kTailThreads, 1) k_coarse_tail(const TailP P)
 {
     pdl_enter();
     extern __shared__ double tail_sh[];
